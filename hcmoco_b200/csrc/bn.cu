@@ -1,0 +1,365 @@
+// Train-mode batch-norm over channels-last activations ([P, C] row-major, P = B*H*W pixels or B*J
+// joints), forward and backward, as HBM-bound column reductions + elementwise passes.
+// Replaces nn.BatchNorm2d(momentum=0.01) (networks/official_hrnet/official_hrnet.py:22-23) and
+// nn.BatchNorm1d (networks/SGCN/sem_gcn.py:13) together with the ReLU / residual-add that follow
+// them (official_hrnet.py:44-60, 86-101).
+//
+// Layout trick: every kernel runs with blockDim.x = the largest multiple of C/VEC <= 256 and walks
+// the flat array with a stride that is a multiple of C, so a thread's channel never changes and no
+// per-element modulo is needed; VEC-wide vector loads keep the accesses coalesced.
+// Reductions are two-level and deterministic: per-CTA fp32 partials -> fp64 finalize.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAXT = 256;
+
+inline int vec_for(long total, int C) { return (C % 4 == 0 && total % 4 == 0) ? 4 : ((C % 2 == 0 && total % 2 == 0) ? 2 : 1); }
+inline int threads_for(int C, int vec) { int cv = C / vec; return (MAXT / cv) * cv; }
+
+template <int VEC> struct VecT;
+template <> struct VecT<1> { typedef float T; };
+template <> struct VecT<2> { typedef float2 T; };
+template <> struct VecT<4> { typedef float4 T; };
+
+template <int VEC>
+__device__ __forceinline__ void vload(const float* p, float (&v)[VEC]) {
+  typename VecT<VEC>::T t = *reinterpret_cast<const typename VecT<VEC>::T*>(p);
+  const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) v[i] = f[i];
+}
+template <int VEC>
+__device__ __forceinline__ void vstore(float* p, const float (&v)[VEC]) {
+  typename VecT<VEC>::T t;
+  float* f = reinterpret_cast<float*>(&t);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) f[i] = v[i];
+  *reinterpret_cast<typename VecT<VEC>::T*>(p) = t;
+}
+
+// ---- column statistics: part[blk][0][c] = sum y, part[blk][1][c] = sum y^2 over the CTA's slice ----
+// MODE 0: plain (y).  MODE 1: backward sums (g, g*yhat) with g = dz * [mask > 0].
+template <int VEC, int MODE>
+__global__ void colstat_kernel(const float* __restrict__ a, const float* __restrict__ y, const float* __restrict__ mask,
+                               const float* __restrict__ mean, const float* __restrict__ invstd, long total, int C,
+                               long per_cta, float* __restrict__ part) {
+  __shared__ float s0[MAXT * 4], s1[MAXT * 4];
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int cv = C / VEC;
+  const int c0 = (t % cv) * VEC;
+  float mu[VEC], is[VEC];
+  if (MODE == 1) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { mu[i] = mean[c0 + i]; is[i] = invstd[c0 + i]; }
+  }
+  float a0[VEC], a1[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
+  const long beg = (long)blockIdx.x * per_cta;
+  const long end = min(total, beg + per_cta);
+  for (long e = beg + (long)t * VEC; e < end; e += (long)nt * VEC) {
+    float v[VEC];
+    vload<VEC>(a + e, v);
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { a0[i] += v[i]; a1[i] = fmaf(v[i], v[i], a1[i]); }
+    } else {
+      float yy[VEC];
+      vload<VEC>(y + e, yy);
+      if (mask) {
+        float m[VEC];
+        vload<VEC>(mask + e, m);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = (m[i] > 0.f) ? v[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { a0[i] += v[i]; a1[i] = fmaf(v[i], (yy[i] - mu[i]) * is[i], a1[i]); }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { s0[t * VEC + i] = a0[i]; s1[t * VEC + i] = a1[i]; }
+  __syncthreads();
+  // threads 0..C-1 fold the copies of their channel: element index j*C + c  <->  thread (j*cv + c/VEC), slot c%VEC
+  if (t < C) {
+    float r0 = 0.f, r1 = 0.f;
+    const int reps = nt / cv;
+    for (int j = 0; j < reps; ++j) {
+      const int idx = (j * cv + t / VEC) * VEC + (t % VEC);
+      r0 += s0[idx]; r1 += s1[idx];
+    }
+    part[((long)blockIdx.x * 2 + 0) * C + t] = r0;
+    part[((long)blockIdx.x * 2 + 1) * C + t] = r1;
+  }
+}
+
+// one warp per channel: fp64 reduction of the partial rows, then the per-channel coefficients
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int nparts, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
+                                   float* scale, float* shift, float* mean_out, float* invstd_out) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int i = lane; i < nparts; i += 32) {
+    s += (double)part[((long)i * 2 + 0) * C + c];
+    q += (double)part[((long)i * 2 + 1) * C + c];
+  }
+  s = warp_sum_d(s); q = warp_sum_d(q);
+  if (lane == 0) {
+    const double m = s / count;
+    double var = q / count - m * m;
+    if (var < 0.0) var = 0.0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    scale[c] = g * is;
+    shift[c] = b - (float)m * g * is;
+    mean_out[c] = (float)m;
+    invstd_out[c] = is;
+    if (running_mean) {
+      const double unb = (count > 1.0) ? var * count / (count - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+  }
+}
+
+// backward finalize: dgamma, dbeta and dy = k1*g + k2*y + k3
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, double count,
+                                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, float* dgamma, float* dbeta, float* k1, float* k2,
+                                       float* k3) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int i = lane; i < nparts; i += 32) {
+    s += (double)part[((long)i * 2 + 0) * C + c];
+    q += (double)part[((long)i * 2 + 1) * C + c];
+  }
+  s = warp_sum_d(s); q = warp_sum_d(q);
+  if (lane == 0) {
+    const float g = gamma ? gamma[c] : 1.f;
+    const double is = invstd[c], mu = mean[c];
+    if (dgamma) dgamma[c] = (float)q;
+    if (dbeta) dbeta[c] = (float)s;
+    const double m1 = s / count, m2 = q / count;
+    const double a = (double)g * is;
+    k1[c] = (float)a;
+    k2[c] = (float)(-a * is * m2);
+    k3[c] = (float)(-a * m1 + a * is * mu * m2);
+  }
+}
+
+// z = act(y*scale + shift + (res*res_scale + res_shift))
+template <int VEC>
+__global__ void bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                                const float* __restrict__ res, const float* __restrict__ res_scale,
+                                const float* __restrict__ res_shift, int relu, float* __restrict__ out, long total, int C) {
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int cv = C / VEC;
+  const int c0 = (t % cv) * VEC;
+  float sc[VEC], sh[VEC], rs[VEC], rh[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    sc[i] = scale ? scale[c0 + i] : 1.f; sh[i] = shift ? shift[c0 + i] : 0.f;
+    rs[i] = res_scale ? res_scale[c0 + i] : 1.f; rh[i] = res_shift ? res_shift[c0 + i] : 0.f;
+  }
+  const long stride = (long)gridDim.x * nt * VEC;
+  for (long e = ((long)blockIdx.x * nt + t) * VEC; e < total; e += stride) {
+    float v[VEC];
+    vload<VEC>(y + e, v);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
+    if (res) {
+      float r[VEC];
+      vload<VEC>(res + e, r);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[i] += fmaf(r[i], rs[i], rh[i]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    vstore<VEC>(out + e, v);
+  }
+}
+
+// g = dz*[mask>0];  dy = k1*g + k2*y + k3;  optionally g_out (+)= g
+template <int VEC>
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ mask, const float* __restrict__ y,
+                                    const float* __restrict__ k1, const float* __restrict__ k2, const float* __restrict__ k3,
+                                    float* __restrict__ dy, float* g_out, int g_accumulate, long total, int C) {
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int cv = C / VEC;
+  const int c0 = (t % cv) * VEC;
+  float a[VEC], b[VEC], c[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { a[i] = k1[c0 + i]; b[i] = k2[c0 + i]; c[i] = k3[c0 + i]; }
+  const long stride = (long)gridDim.x * nt * VEC;
+  for (long e = ((long)blockIdx.x * nt + t) * VEC; e < total; e += stride) {
+    float g[VEC], yy[VEC], o[VEC];
+    vload<VEC>(dz + e, g);
+    vload<VEC>(y + e, yy);
+    if (mask) {
+      float m[VEC];
+      vload<VEC>(mask + e, m);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) g[i] = (m[i] > 0.f) ? g[i] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = fmaf(a[i], g[i], fmaf(b[i], yy[i], c[i]));
+    vstore<VEC>(dy + e, o);
+    if (g_out) {
+      if (g_accumulate) {
+        float old[VEC];
+        vload<VEC>(g_out + e, old);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) g[i] += old[i];
+      }
+      vstore<VEC>(g_out + e, g);
+    }
+  }
+}
+
+// generic elementwise helpers (float4 main body + scalar tail)
+__global__ void relu_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, float* g, int accumulate,
+                                long total) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    float v = (out[e] > 0.f) ? dout[e] : 0.f;
+    g[e] = accumulate ? g[e] + v : v;
+  }
+}
+__global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, float alpha, long total) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) dst[e] = fmaf(alpha, src[e], dst[e]);
+}
+
+inline int ew_grid(long total, int per_thread_elems, int threads) {
+  long g = (total + (long)threads * per_thread_elems - 1) / ((long)threads * per_thread_elems);
+  long cap = 148L * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+inline void colstat_plan(long total, int C, int* vec, int* threads, int* nparts, long* per_cta) {
+  *vec = vec_for(total, C);
+  *threads = threads_for(C, *vec);
+  long unit = (long)(*threads) * (*vec);           // multiple of C
+  long want = 148L * 4;
+  long units = (total + unit - 1) / unit;
+  long per = (units + want - 1) / want;
+  if (per < 4) per = (units < 4) ? units : 4;
+  if (per < 1) per = 1;
+  *per_cta = per * unit;
+  *nparts = (int)((total + *per_cta - 1) / *per_cta);
+}
+
+}  // namespace
+
+extern "C" {
+
+int hcm_colstat_rows(long P, int C) {
+  int vec, threads, nparts;
+  long per;
+  colstat_plan(P * C, C, &vec, &threads, &nparts, &per);
+  return nparts;
+}
+
+// part [hcm_colstat_rows][2][C]: per-CTA sums of y and y^2
+int hcm_bn_stats(const float* y, long P, int C, float* part, cudaStream_t stream) {
+  HCM_CHECK_ARG(y && part && C >= 1 && C <= 256, "bn_stats: bad args (C=%d)", C);
+  int vec, threads, nparts;
+  long per;
+  const long total = P * C;
+  colstat_plan(total, C, &vec, &threads, &nparts, &per);
+  if (vec == 4) colstat_kernel<4, 0><<<nparts, threads, 0, stream>>>(y, nullptr, nullptr, nullptr, nullptr, total, C, per, part);
+  else if (vec == 2) colstat_kernel<2, 0><<<nparts, threads, 0, stream>>>(y, nullptr, nullptr, nullptr, nullptr, total, C, per, part);
+  else colstat_kernel<1, 0><<<nparts, threads, 0, stream>>>(y, nullptr, nullptr, nullptr, nullptr, total, C, per, part);
+  HCM_LAUNCH_CHECK("bn_stats");
+  return HCM_OK;
+}
+
+int hcm_bn_finalize(const float* part, int nparts, int C, long count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                    float* scale, float* shift, float* mean, float* invstd, cudaStream_t stream) {
+  HCM_CHECK_ARG(part && scale && shift && mean && invstd && nparts >= 1, "bn_finalize: bad args");
+  bn_finalize_kernel<<<hcm_cdiv(C, 4), 128, 0, stream>>>(part, nparts, C, (double)count, gamma, beta, running_mean,
+                                                         running_var, num_batches_tracked, momentum, eps, scale, shift,
+                                                         mean, invstd);
+  HCM_LAUNCH_CHECK("bn_finalize");
+  return HCM_OK;
+}
+
+int hcm_bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* res_scale,
+                 const float* res_shift, int relu, float* out, long P, int C, cudaStream_t stream) {
+  HCM_CHECK_ARG(y && out && C >= 1 && C <= 256, "bn_apply: bad args (C=%d)", C);
+  const long total = P * C;
+  const int vec = vec_for(total, C), threads = threads_for(C, vec);
+  const int grid = ew_grid(total, vec * 4, threads);
+  if (vec == 4) bn_apply_kernel<4><<<grid, threads, 0, stream>>>(y, scale, shift, res, res_scale, res_shift, relu, out, total, C);
+  else if (vec == 2) bn_apply_kernel<2><<<grid, threads, 0, stream>>>(y, scale, shift, res, res_scale, res_shift, relu, out, total, C);
+  else bn_apply_kernel<1><<<grid, threads, 0, stream>>>(y, scale, shift, res, res_scale, res_shift, relu, out, total, C);
+  HCM_LAUNCH_CHECK("bn_apply");
+  return HCM_OK;
+}
+
+// part [hcm_colstat_rows][2][C]: per-CTA sums of g and g*yhat, g = dz*[mask>0] (mask may be null)
+int hcm_bn_bwd_reduce(const float* dz, const float* mask, const float* y, const float* mean, const float* invstd, long P,
+                      int C, float* part, cudaStream_t stream) {
+  HCM_CHECK_ARG(dz && y && mean && invstd && part && C >= 1 && C <= 256, "bn_bwd_reduce: bad args (C=%d)", C);
+  int vec, threads, nparts;
+  long per;
+  const long total = P * C;
+  colstat_plan(total, C, &vec, &threads, &nparts, &per);
+  if (vec == 4) colstat_kernel<4, 1><<<nparts, threads, 0, stream>>>(dz, y, mask, mean, invstd, total, C, per, part);
+  else if (vec == 2) colstat_kernel<2, 1><<<nparts, threads, 0, stream>>>(dz, y, mask, mean, invstd, total, C, per, part);
+  else colstat_kernel<1, 1><<<nparts, threads, 0, stream>>>(dz, y, mask, mean, invstd, total, C, per, part);
+  HCM_LAUNCH_CHECK("bn_bwd_reduce");
+  return HCM_OK;
+}
+
+int hcm_bn_bwd_finalize(const float* part, int nparts, int C, long count, const float* gamma, const float* mean,
+                        const float* invstd, float* dgamma, float* dbeta, float* k1, float* k2, float* k3,
+                        cudaStream_t stream) {
+  HCM_CHECK_ARG(part && mean && invstd && k1 && k2 && k3, "bn_bwd_finalize: bad args");
+  bn_bwd_finalize_kernel<<<hcm_cdiv(C, 4), 128, 0, stream>>>(part, nparts, C, (double)count, gamma, mean, invstd, dgamma,
+                                                             dbeta, k1, k2, k3);
+  HCM_LAUNCH_CHECK("bn_bwd_finalize");
+  return HCM_OK;
+}
+
+int hcm_bn_bwd_apply(const float* dz, const float* mask, const float* y, const float* k1, const float* k2,
+                     const float* k3, float* dy, float* g_out, int g_accumulate, long P, int C, cudaStream_t stream) {
+  HCM_CHECK_ARG(dz && y && k1 && k2 && k3 && dy && C >= 1 && C <= 256, "bn_bwd_apply: bad args (C=%d)", C);
+  const long total = P * C;
+  const int vec = vec_for(total, C), threads = threads_for(C, vec);
+  const int grid = ew_grid(total, vec * 4, threads);
+  if (vec == 4) bn_bwd_apply_kernel<4><<<grid, threads, 0, stream>>>(dz, mask, y, k1, k2, k3, dy, g_out, g_accumulate, total, C);
+  else if (vec == 2) bn_bwd_apply_kernel<2><<<grid, threads, 0, stream>>>(dz, mask, y, k1, k2, k3, dy, g_out, g_accumulate, total, C);
+  else bn_bwd_apply_kernel<1><<<grid, threads, 0, stream>>>(dz, mask, y, k1, k2, k3, dy, g_out, g_accumulate, total, C);
+  HCM_LAUNCH_CHECK("bn_bwd_apply");
+  return HCM_OK;
+}
+
+// g (+)= dout * [out > 0]
+int hcm_relu_bwd(const float* dout, const float* out, float* g, int accumulate, long total, cudaStream_t stream) {
+  HCM_CHECK_ARG(dout && out && g, "relu_bwd: null pointer");
+  relu_bwd_kernel<<<ew_grid(total, 4, 256), 256, 0, stream>>>(dout, out, g, accumulate, total);
+  HCM_LAUNCH_CHECK("relu_bwd");
+  return HCM_OK;
+}
+
+// dst += alpha * src
+int hcm_axpy(float* dst, const float* src, float alpha, long total, cudaStream_t stream) {
+  HCM_CHECK_ARG(dst && src, "axpy: null pointer");
+  axpy_kernel<<<ew_grid(total, 4, 256), 256, 0, stream>>>(dst, src, alpha, total);
+  HCM_LAUNCH_CHECK("axpy");
+  return HCM_OK;
+}
+
+}  // extern "C"

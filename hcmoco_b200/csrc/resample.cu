@@ -1,0 +1,224 @@
+// Layout / resampling kernels around the HRNet cross-resolution fuse and the model head:
+//   * NCHW -> NHWC split of the [B,6,R,R] input (build_backbone.py:261 torch.split)
+//   * fuse_sum: out = act( sum_t  affine_t( bilinear_up_{2^k}(term_t) ) + bias ) — the HR-module fuse
+//     (official_hrnet.py:232-247, F.interpolate(mode='bilinear', align_corners=False)) and the 4-branch
+//     merge feeding the 1x1 projection (build_backbone.py:247-254, 291-294).  BN's per-channel affine
+//     commutes with bilinear interpolation (weights sum to 1), so the low-resolution raw conv output is
+//     interpolated and the affine applied once at the high resolution.
+//   * upsample_adjoint: exact transpose of the bilinear upsampling, as a deterministic gather
+//   * global average pool (+ backward) (build_backbone.py:267-278)
+#include "common.cuh"
+
+namespace {
+
+struct FuseTerm {
+  const float* ptr;
+  const float* scale;  // per channel, null -> 1
+  const float* shift;  // per channel, null -> 0
+  int log2f;           // 0: same resolution; k: source is (H>>k) x (W>>k), bilinear up by 2^k
+};
+struct FuseParams {
+  FuseTerm t[4];
+  int nterms;
+  const float* bias;
+  int relu;
+  float* out;
+  int B, H, W, C;
+};
+
+// PyTorch upsample_bilinear2d, align_corners=False, scale = in/out = 1/f
+__device__ __forceinline__ void src_index(int dst, int f, int in_size, int& i0, int& i1, float& l1) {
+  float s = ((float)dst + 0.5f) / (float)f - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = s - (float)i0;
+}
+
+__global__ void fuse_sum_kernel(const FuseParams p) {
+  const long total = (long)p.B * p.H * p.W * p.C;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int c = (int)(e % p.C);
+    long pix = e / p.C;
+    const int w = (int)(pix % p.W);
+    pix /= p.W;
+    const int h = (int)(pix % p.H);
+    const int b = (int)(pix / p.H);
+    float acc = p.bias ? p.bias[c] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (t >= p.nterms) break;
+      const FuseTerm& T = p.t[t];
+      float v;
+      if (T.log2f == 0) {
+        v = T.ptr[e];
+      } else {
+        const int f = 1 << T.log2f;
+        const int Hs = p.H >> T.log2f, Ws = p.W >> T.log2f;
+        int y0, y1, x0, x1;
+        float ly, lx;
+        src_index(h, f, Hs, y0, y1, ly);
+        src_index(w, f, Ws, x0, x1, lx);
+        const float* base = T.ptr + (long)b * Hs * Ws * p.C + c;
+        const float v00 = base[((long)y0 * Ws + x0) * p.C], v01 = base[((long)y0 * Ws + x1) * p.C];
+        const float v10 = base[((long)y1 * Ws + x0) * p.C], v11 = base[((long)y1 * Ws + x1) * p.C];
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        v = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+      }
+      if (T.scale) v = fmaf(v, T.scale[c], T.shift ? T.shift[c] : 0.f);
+      acc += v;
+    }
+    if (p.relu) acc = fmaxf(acc, 0.f);
+    p.out[e] = acc;
+  }
+}
+
+// out[b,Y,X,c] (+)= sum over high-res (h,w) of weight(h->Y)*weight(w->X) * g[b,h,w,c]
+__global__ void upsample_adjoint_kernel(const float* __restrict__ g, float* out, int accumulate, int B, int H, int W, int C,
+                                        int log2f) {
+  const int f = 1 << log2f;
+  const int Hs = H >> log2f, Ws = W >> log2f;
+  const long total = (long)B * Hs * Ws * C;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int c = (int)(e % C);
+    long pix = e / C;
+    const int X = (int)(pix % Ws);
+    pix /= Ws;
+    const int Y = (int)(pix % Hs);
+    const int b = (int)(pix / Hs);
+    // candidate high-res rows: those whose y0 or y1 can equal Y
+    const int hlo = max(0, f * Y - f), hhi = min(H - 1, f * Y + 2 * f - 1);
+    const int wlo = max(0, f * X - f), whi = min(W - 1, f * X + 2 * f - 1);
+    float acc = 0.f;
+    for (int h = hlo; h <= hhi; ++h) {
+      int y0, y1;
+      float ly;
+      src_index(h, f, Hs, y0, y1, ly);
+      float wy = 0.f;
+      if (y0 == Y) wy += 1.f - ly;
+      if (y1 == Y) wy += ly;
+      if (wy == 0.f) continue;
+      const float* row = g + ((long)(b * H + h) * W) * C + c;
+      float racc = 0.f;
+      for (int w = wlo; w <= whi; ++w) {
+        int x0, x1;
+        float lx;
+        src_index(w, f, Ws, x0, x1, lx);
+        float wx = 0.f;
+        if (x0 == X) wx += 1.f - lx;
+        if (x1 == X) wx += lx;
+        if (wx != 0.f) racc = fmaf(wx, row[(long)w * C], racc);
+      }
+      acc = fmaf(wy, racc, acc);
+    }
+    out[e] = accumulate ? out[e] + acc : acc;
+  }
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int Ctot, long HW, int coff,
+                                    int Cn) {
+  const long total = (long)B * HW;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const long b = e / HW, pix = e - b * HW;
+    for (int c = 0; c < Cn; ++c) out[e * Cn + c] = x[(b * Ctot + coff + c) * HW + pix];
+  }
+}
+
+// one CTA per sample; blockDim multiple of C so a thread's channel is fixed
+__global__ void avgpool_kernel(const float* __restrict__ x, float* out, long HW, int C, int ldo, int coff) {
+  __shared__ float sm[256];
+  const int t = threadIdx.x, nt = blockDim.x;
+  const float* xb = x + (long)blockIdx.x * HW * C;
+  float a = 0.f;
+  for (long e = t; e < HW * C; e += nt) a += xb[e];
+  sm[t] = a;
+  __syncthreads();
+  if (t < C) {
+    float r = 0.f;
+    for (int j = t; j < nt; j += C) r += sm[j];
+    out[(long)blockIdx.x * ldo + coff + t] = r / (float)HW;
+  }
+}
+
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dout, float* dx, int accumulate, int B, long HW, int C, int ldo,
+                                   int coff) {
+  const long total = (long)B * HW * C;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const float inv = 1.f / (float)HW;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int c = (int)(e % C);
+    const long b = e / (HW * C);
+    const float v = dout[b * ldo + coff + c] * inv;
+    dx[e] = accumulate ? dx[e] + v : v;
+  }
+}
+
+inline int ew_grid(long total) {
+  long g = (total + 1023) / 1024;
+  if (g > 148L * 16) g = 148L * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" {
+
+// out[B,HW,Cn] (NHWC) = x[B, coff:coff+Cn, HW] (NCHW)
+int hcm_nchw_to_nhwc(const float* x, float* out, int B, int Ctot, long HW, int coff, int Cn, cudaStream_t stream) {
+  HCM_CHECK_ARG(x && out && coff + Cn <= Ctot, "nchw_to_nhwc: bad args");
+  nchw_to_nhwc_kernel<<<ew_grid((long)B * HW * 4), 256, 0, stream>>>(x, out, B, Ctot, HW, coff, Cn);
+  HCM_LAUNCH_CHECK("nchw_to_nhwc");
+  return HCM_OK;
+}
+
+// terms: up to 4 (ptr, scale, shift, log2 factor); out [B,H,W,C]
+int hcm_fuse_sum(int nterms, const float* const* ptrs, const float* const* scales, const float* const* shifts,
+                 const int* log2f, const float* bias, int relu, float* out, int B, int H, int W, int C,
+                 cudaStream_t stream) {
+  HCM_CHECK_ARG(nterms >= 1 && nterms <= 4 && out, "fuse_sum: nterms=%d", nterms);
+  FuseParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < nterms; ++i) {
+    HCM_CHECK_ARG(ptrs[i] != nullptr, "fuse_sum: null term %d", i);
+    HCM_CHECK_ARG(log2f[i] >= 0 && (H >> log2f[i]) >= 1 && ((H >> log2f[i]) << log2f[i]) == H &&
+                  ((W >> log2f[i]) << log2f[i]) == W, "fuse_sum: size not divisible by 2^%d", log2f[i]);
+    p.t[i].ptr = ptrs[i];
+    p.t[i].scale = scales ? scales[i] : nullptr;
+    p.t[i].shift = shifts ? shifts[i] : nullptr;
+    p.t[i].log2f = log2f[i];
+  }
+  p.nterms = nterms; p.bias = bias; p.relu = relu; p.out = out; p.B = B; p.H = H; p.W = W; p.C = C;
+  fuse_sum_kernel<<<ew_grid((long)B * H * W * C), 256, 0, stream>>>(p);
+  HCM_LAUNCH_CHECK("fuse_sum");
+  return HCM_OK;
+}
+
+// g [B,H,W,C] high-res gradient -> out [B,H>>k,W>>k,C]
+int hcm_upsample_adjoint(const float* g, float* out, int accumulate, int B, int H, int W, int C, int log2f,
+                         cudaStream_t stream) {
+  HCM_CHECK_ARG(g && out && log2f >= 1, "upsample_adjoint: bad args");
+  upsample_adjoint_kernel<<<ew_grid(((long)B * H * W * C) >> (2 * log2f)), 256, 0, stream>>>(g, out, accumulate, B, H, W, C, log2f);
+  HCM_LAUNCH_CHECK("upsample_adjoint");
+  return HCM_OK;
+}
+
+int hcm_avgpool(const float* x, float* out, int B, long HW, int C, int ldo, int coff, cudaStream_t stream) {
+  HCM_CHECK_ARG(x && out && C >= 1 && C <= 256, "avgpool: bad args (C=%d)", C);
+  avgpool_kernel<<<B, (256 / C) * C, 0, stream>>>(x, out, HW, C, ldo, coff);
+  HCM_LAUNCH_CHECK("avgpool");
+  return HCM_OK;
+}
+
+int hcm_avgpool_bwd(const float* dout, float* dx, int accumulate, int B, long HW, int C, int ldo, int coff,
+                    cudaStream_t stream) {
+  HCM_CHECK_ARG(dout && dx, "avgpool_bwd: null pointer");
+  avgpool_bwd_kernel<<<ew_grid((long)B * HW * C), 256, 0, stream>>>(dout, dx, accumulate, B, HW, C, ldo, coff);
+  HCM_LAUNCH_CHECK("avgpool_bwd");
+  return HCM_OK;
+}
+
+}  // extern "C"

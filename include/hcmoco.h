@@ -1,0 +1,134 @@
+/* hcmoco.h — C-ABI of libhcmoco_sm100.so: the sm_100a kernels behind the HCMoCo pre-train step.
+ *
+ * The reference has no FFI on this path (it is PyTorch eager end to end); this ABI is the seam one
+ * level below the Python surface main_contrast.py uses.  Each entry point names the
+ * reference call site it replaces (paths relative to pycontrast/ in hongfz16/HCMoCo).
+ *
+ * Conventions
+ *   - all tensors are device pointers owned by the caller; the library never allocates, frees or
+ *     keeps a pointer after the call returns; scratch buffers are passed in (sizes documented);
+ *   - activations are channels-last fp32: [B, H, W, C] (or [rows, C]); conv weights keep the
+ *     reference / checkpoint layout OIHW; indices are int64 as torch produces them;
+ *   - every call only enqueues work on `stream` (no sync, no default-stream use) => composes with
+ *     CUDA graphs and side streams;
+ *   - return 0 on success, negative on error (HCM_ERR_*); hcm_last_error() gives a thread-local text.
+ */
+#ifndef HCMOCO_H_
+#define HCMOCO_H_
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int hcm_abi_version(void);
+const char* hcm_last_error(void);
+
+/* ---- convolutions / GEMM (igemm.cu) : nn.Conv2d in networks/official_hrnet/official_hrnet.py:26-29,
+ *      68-75, 187-216, 336-357 ; nn.Linear / 1x1 projection in networks/build_backbone.py:226-245 ---- */
+/* y[B,Ho,Wo,Cout] = conv(T(x[B,H,W,Cin]), w[Cout,Cin,ks,ks]) (+bias); pad=(ks-1)/2; ks in {1,3}; stride in {1,2}.
+ * T = optional per-channel affine (+ReLU) applied on load (= the previous layer's BatchNorm).
+ * stat_part (optional) [hcm_conv2d_stat_rows()][2][Cout]: per-CTA column sums of y and y^2 for train-mode BN. */
+int hcm_conv2d_stat_rows(int B, int H, int W, int Cin, int Cout, int ks, int stride);
+int hcm_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
+                   int Cout, int ks, int stride, const float* in_scale, const float* in_shift, int in_relu,
+                   float* stat_part, cudaStream_t stream);
+/* dx[B,H,W,Cin] (+)= conv_transpose(dy[B,Ho,Wo,Cout], w) */
+int hcm_conv2d_dgrad(const float* dy, const float* w, float* dx, int B, int H, int W, int Cin, int Cout, int ks,
+                     int stride, int accumulate, cudaStream_t stream);
+/* dw[Cout,Cin,ks,ks] += sum_pixels dy * T(x)   (fp32 reductions; caller zeroes dw once per step) */
+int hcm_conv2d_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int Cout, int ks,
+                     int stride, const float* in_scale, const float* in_shift, int in_relu, cudaStream_t stream);
+/* C[b][m][n] = alpha * sum_k A[b*bsA + m*sAm + k*sAk] * B[b*bsB + k*sBk + n*sBn] (+bias[n]) (+C) ; C row stride sCm */
+int hcm_gemm(const float* A, const float* Bm, const float* bias, float* C, int batch, int M, int N, int K, long sAm,
+             long sAk, long sBk, long sBn, long sCm, long bsA, long bsB, long bsC, float alpha, int accumulate,
+             cudaStream_t stream);
+
+/* ---- train-mode batch norm (bn.cu) : nn.BatchNorm2d(momentum=0.01) official_hrnet.py:22-23 (+ReLU /
+ *      residual add :44-60, :86-101) and nn.BatchNorm1d networks/SGCN/sem_gcn.py:13 ---- */
+int hcm_colstat_rows(long P, int C);
+int hcm_bn_stats(const float* y, long P, int C, float* part, cudaStream_t stream);
+int hcm_bn_finalize(const float* part, int nparts, int C, long count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                    float* scale, float* shift, float* mean, float* invstd, cudaStream_t stream);
+/* out = act(y*scale + shift + (res*res_scale + res_shift)) */
+int hcm_bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* res_scale,
+                 const float* res_shift, int relu, float* out, long P, int C, cudaStream_t stream);
+int hcm_bn_bwd_reduce(const float* dz, const float* mask, const float* y, const float* mean, const float* invstd, long P,
+                      int C, float* part, cudaStream_t stream);
+int hcm_bn_bwd_finalize(const float* part, int nparts, int C, long count, const float* gamma, const float* mean,
+                        const float* invstd, float* dgamma, float* dbeta, float* k1, float* k2, float* k3,
+                        cudaStream_t stream);
+/* g = dz*[mask>0]; dy = k1*g + k2*y + k3; g_out (+)= g (gradient of the residual branch) */
+int hcm_bn_bwd_apply(const float* dz, const float* mask, const float* y, const float* k1, const float* k2,
+                     const float* k3, float* dy, float* g_out, int g_accumulate, long P, int C, cudaStream_t stream);
+int hcm_relu_bwd(const float* dout, const float* out, float* g, int accumulate, long total, cudaStream_t stream);
+int hcm_axpy(float* dst, const float* src, float alpha, long total, cudaStream_t stream);
+
+/* ---- layout / resampling (resample.cu) : torch.split build_backbone.py:261; HR-module fuse
+ *      official_hrnet.py:232-247; merge_all_res build_backbone.py:247-254; avg-pool :267-278 ---- */
+int hcm_nchw_to_nhwc(const float* x, float* out, int B, int Ctot, long HW, int coff, int Cn, cudaStream_t stream);
+int hcm_fuse_sum(int nterms, const float* const* ptrs, const float* const* scales, const float* const* shifts,
+                 const int* log2f, const float* bias, int relu, float* out, int B, int H, int W, int C,
+                 cudaStream_t stream);
+int hcm_upsample_adjoint(const float* g, float* out, int accumulate, int B, int H, int W, int C, int log2f,
+                         cudaStream_t stream);
+int hcm_avgpool(const float* x, float* out, int B, long HW, int C, int ldo, int coff, cudaStream_t stream);
+int hcm_avgpool_bwd(const float* dout, float* dx, int accumulate, int B, long HW, int C, int ldo, int coff,
+                    cudaStream_t stream);
+
+/* ---- memory-bank NCE (nce.cu) : CMCMem3.forward memory/mem_bank.py:172-205, _update_memory :15-28,
+ *      _compute_loss_accuracy learning/contrast_trainer.py:212-253 ---- */
+int hcm_nce_logits(const float* bank1, const float* bank2, const float* bank3, const float* x1, const float* x2,
+                   const float* x3, long ldx, const long long* idx, int B, int K1, int dim, float T, float* logits,
+                   cudaStream_t stream);
+int hcm_nce_loss(const float* logits, int B, int K1, const long long* use_depth, const long long* use_rgb, float* lse,
+                 float* l0, float* hit, float* coef, float* loss6, float* acc6, cudaStream_t stream);
+int hcm_nce_bwd(const float* bank1, const float* bank2, const float* bank3, const float* x1, const float* x2,
+                const float* x3, long ldx, const long long* idx, int B, int K1, int dim, float T, const float* logits,
+                const float* lse, const float* coef, float gscale, float* df, long lddf, cudaStream_t stream);
+int hcm_bank_update(float* bank, const float* x, long ldx, const long long* y, int N, int dim, float m,
+                    cudaStream_t stream);
+
+/* ---- dense / sparse / SCL objectives (losses.cu) : contrast_trainer.py:642-723, 744-828, 830-892 ---- */
+int hcm_gather_l2norm(const float* src, long lds, const long long* pix, long HW, int rows_per_b, long nrows, int dim,
+                      float* out, long ldo, float* inv_norm, cudaStream_t stream);
+int hcm_gather_l2norm_bwd(const float* dout, long lddo, const float* out, long ldo, const float* inv_norm,
+                          const long long* pix, long HW, int rows_per_b, long nrows, int dim, float* dsrc, long lds,
+                          int accumulate, cudaStream_t stream);
+int hcm_joint_pixel_index(const float* joints_yx, long n, int h, long long* pix, cudaStream_t stream);
+int hcm_dense_kept(const float* depth_mask, int B, int R, int h, float* kept, cudaStream_t stream);
+int hcm_dense_stats(const float* L, const long long* pix, const float* kept, const long long* use_depth, int B, int S,
+                    int h, float* stat, float* fin, cudaStream_t stream);
+int hcm_dense_grad(float* L, const long long* pix, const float* stat, const float* kept, const float* fin, int B, int S,
+                   int h, float gscale, cudaStream_t stream);
+int hcm_joint_stats(const float* Lr, const float* Ld, const int* joints_vis, const long long* use_depth, int B, int J,
+                    float* rs, float* lse, float* fin, cudaStream_t stream);
+int hcm_joint_grad(float* Lr, float* Ld, const int* joints_vis, const long long* use_depth, const float* lse,
+                   const float* fin, int B, int J, float gscale, cudaStream_t stream);
+int hcm_scl_stats(const float* Z, int B, int J, const long long* use_rgb, const long long* use_depth, float* rowstat,
+                  float* fin, cudaStream_t stream);
+int hcm_scl_grad(float* Z, int B, int J, const long long* use_rgb, const long long* use_depth, const float* rowstat,
+                 const float* fin, float gscale, cudaStream_t stream);
+int hcm_colsum_finalize(const float* part, int nparts, int C, float* out, int accumulate, cudaStream_t stream);
+int hcm_colsum_small(const float* x, int R, int C, long ld, float* out, int accumulate, cudaStream_t stream);
+
+/* ---- SemGCN graph side + optimiser (sgcn.cu) : networks/SGCN/sem_graph_conv.py:34-48;
+ *      torch.optim.SGD main_contrast.py:78-81 ---- */
+int hcm_sgcn_adj(const float* e, const int* rows, const int* cols, int nnz, int J, float* A, cudaStream_t stream);
+int hcm_sgcn_adj_bwd(const float* A, const float* dA, const int* rows, const int* cols, int nnz, int J, float* de,
+                     int accumulate, cudaStream_t stream);
+int hcm_sgcn_aggregate(const float* x, const float* A, int B, int J, int Cin, float* xa, cudaStream_t stream);
+int hcm_sgcn_aggregate_bwd(const float* dxa, const float* x, const float* A, int B, int J, int Cin, float* dx,
+                           int accumulate, float* dA, cudaStream_t stream);
+int hcm_joint_mean(const float* x, int B, int J, int C, float* out, cudaStream_t stream);
+int hcm_joint_mean_bwd(const float* dout, int B, int J, int C, float* dx, int accumulate, cudaStream_t stream);
+int hcm_sgd_step(float* p, const float* g, float* buf, long n, float lr, float momentum, float wd, int first,
+                 float gscale, cudaStream_t stream);
+int hcm_zero(void* p, long bytes, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HCMOCO_H_ */
