@@ -42,16 +42,20 @@ __device__ __forceinline__ void vstore(float* p, const float (&v)[VEC]) {
 // MODE 0: plain (y).  MODE 1: backward sums (g, g*yhat) with g = dz * [mask > 0].
 template <int VEC, int MODE>
 __global__ void colstat_kernel(const float* __restrict__ a, const float* __restrict__ y, const float* __restrict__ mask,
-                               const float* __restrict__ mean, const float* __restrict__ invstd, long total, int C,
+                               const float* __restrict__ mean, const float* __restrict__ invstd,
+                               const float* __restrict__ msc, const float* __restrict__ msh, long total, int C,
                                long per_cta, float* __restrict__ part) {
   __shared__ float s0[MAXT * 4], s1[MAXT * 4];
   const int t = threadIdx.x, nt = blockDim.x;
   const int cv = C / VEC;
   const int c0 = (t % cv) * VEC;
-  float mu[VEC], is[VEC];
+  float mu[VEC], is[VEC], ms[VEC], mh[VEC];
   if (MODE == 1) {
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { mu[i] = mean[c0 + i]; is[i] = invstd[c0 + i]; }
+    for (int i = 0; i < VEC; ++i) {
+      mu[i] = mean[c0 + i]; is[i] = invstd[c0 + i];
+      ms[i] = msc ? msc[c0 + i] : 0.f; mh[i] = msc ? msh[c0 + i] : 0.f;
+    }
   }
   float a0[VEC], a1[VEC];
 #pragma unroll
@@ -72,6 +76,9 @@ __global__ void colstat_kernel(const float* __restrict__ a, const float* __restr
         vload<VEC>(mask + e, m);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) v[i] = (m[i] > 0.f) ? v[i] : 0.f;
+      } else if (msc) {  // ReLU mask recomputed from the raw conv output: relu(y*scale+shift) > 0
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = (fmaf(yy[i], ms[i], mh[i]) > 0.f) ? v[i] : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < VEC; ++i) { a0[i] += v[i]; a1[i] = fmaf(v[i], (yy[i] - mu[i]) * is[i], a1[i]); }
@@ -189,15 +196,19 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, const float* __rest
 
 // g = dz*[mask>0];  dy = k1*g + k2*y + k3;  optionally g_out (+)= g
 template <int VEC>
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ mask, const float* __restrict__ y,
+__global__ void bn_bwd_apply_kernel(const float* dz, const float* __restrict__ mask, const float* __restrict__ y,
+                                    const float* __restrict__ msc, const float* __restrict__ msh,
                                     const float* __restrict__ k1, const float* __restrict__ k2, const float* __restrict__ k3,
-                                    float* __restrict__ dy, float* g_out, int g_accumulate, long total, int C) {
+                                    float* dy, float* g_out, int g_accumulate, long total, int C) {
   const int t = threadIdx.x, nt = blockDim.x;
   const int cv = C / VEC;
   const int c0 = (t % cv) * VEC;
-  float a[VEC], b[VEC], c[VEC];
+  float a[VEC], b[VEC], c[VEC], ms[VEC], mh[VEC];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) { a[i] = k1[c0 + i]; b[i] = k2[c0 + i]; c[i] = k3[c0 + i]; }
+  for (int i = 0; i < VEC; ++i) {
+    a[i] = k1[c0 + i]; b[i] = k2[c0 + i]; c[i] = k3[c0 + i];
+    ms[i] = msc ? msc[c0 + i] : 0.f; mh[i] = msc ? msh[c0 + i] : 0.f;
+  }
   const long stride = (long)gridDim.x * nt * VEC;
   for (long e = ((long)blockIdx.x * nt + t) * VEC; e < total; e += stride) {
     float g[VEC], yy[VEC], o[VEC];
@@ -208,6 +219,9 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* _
       vload<VEC>(mask + e, m);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) g[i] = (m[i] > 0.f) ? g[i] : 0.f;
+    } else if (msc) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) g[i] = (fmaf(yy[i], ms[i], mh[i]) > 0.f) ? g[i] : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < VEC; ++i) o[i] = fmaf(a[i], g[i], fmaf(b[i], yy[i], c[i]));
@@ -277,9 +291,9 @@ int hcm_bn_stats(const float* y, long P, int C, float* part, cudaStream_t stream
   long per;
   const long total = P * C;
   colstat_plan(total, C, &vec, &threads, &nparts, &per);
-  if (vec == 4) colstat_kernel<4, 0><<<nparts, threads, 0, stream>>>(y, nullptr, nullptr, nullptr, nullptr, total, C, per, part);
-  else if (vec == 2) colstat_kernel<2, 0><<<nparts, threads, 0, stream>>>(y, nullptr, nullptr, nullptr, nullptr, total, C, per, part);
-  else colstat_kernel<1, 0><<<nparts, threads, 0, stream>>>(y, nullptr, nullptr, nullptr, nullptr, total, C, per, part);
+  if (vec == 4) colstat_kernel<4, 0><<<nparts, threads, 0, stream>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, total, C, per, part);
+  else if (vec == 2) colstat_kernel<2, 0><<<nparts, threads, 0, stream>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, total, C, per, part);
+  else colstat_kernel<1, 0><<<nparts, threads, 0, stream>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, total, C, per, part);
   HCM_LAUNCH_CHECK("bn_stats");
   return HCM_OK;
 }
@@ -309,16 +323,17 @@ int hcm_bn_apply(const float* y, const float* scale, const float* shift, const f
 }
 
 // part [hcm_colstat_rows][2][C]: per-CTA sums of g and g*yhat, g = dz*[mask>0] (mask may be null)
-int hcm_bn_bwd_reduce(const float* dz, const float* mask, const float* y, const float* mean, const float* invstd, long P,
-                      int C, float* part, cudaStream_t stream) {
+int hcm_bn_bwd_reduce(const float* dz, const float* mask, const float* mask_scale, const float* mask_shift,
+                      const float* y, const float* mean, const float* invstd, long P, int C, float* part,
+                      cudaStream_t stream) {
   HCM_CHECK_ARG(dz && y && mean && invstd && part && C >= 1 && C <= 256, "bn_bwd_reduce: bad args (C=%d)", C);
   int vec, threads, nparts;
   long per;
   const long total = P * C;
   colstat_plan(total, C, &vec, &threads, &nparts, &per);
-  if (vec == 4) colstat_kernel<4, 1><<<nparts, threads, 0, stream>>>(dz, y, mask, mean, invstd, total, C, per, part);
-  else if (vec == 2) colstat_kernel<2, 1><<<nparts, threads, 0, stream>>>(dz, y, mask, mean, invstd, total, C, per, part);
-  else colstat_kernel<1, 1><<<nparts, threads, 0, stream>>>(dz, y, mask, mean, invstd, total, C, per, part);
+  if (vec == 4) colstat_kernel<4, 1><<<nparts, threads, 0, stream>>>(dz, y, mask, mean, invstd, mask_scale, mask_shift, total, C, per, part);
+  else if (vec == 2) colstat_kernel<2, 1><<<nparts, threads, 0, stream>>>(dz, y, mask, mean, invstd, mask_scale, mask_shift, total, C, per, part);
+  else colstat_kernel<1, 1><<<nparts, threads, 0, stream>>>(dz, y, mask, mean, invstd, mask_scale, mask_shift, total, C, per, part);
   HCM_LAUNCH_CHECK("bn_bwd_reduce");
   return HCM_OK;
 }
@@ -333,15 +348,16 @@ int hcm_bn_bwd_finalize(const float* part, int nparts, int C, long count, const 
   return HCM_OK;
 }
 
-int hcm_bn_bwd_apply(const float* dz, const float* mask, const float* y, const float* k1, const float* k2,
-                     const float* k3, float* dy, float* g_out, int g_accumulate, long P, int C, cudaStream_t stream) {
+int hcm_bn_bwd_apply(const float* dz, const float* mask, const float* mask_scale, const float* mask_shift,
+                     const float* y, const float* k1, const float* k2, const float* k3, float* dy, float* g_out,
+                     int g_accumulate, long P, int C, cudaStream_t stream) {
   HCM_CHECK_ARG(dz && y && k1 && k2 && k3 && dy && C >= 1 && C <= 256, "bn_bwd_apply: bad args (C=%d)", C);
   const long total = P * C;
   const int vec = vec_for(total, C), threads = threads_for(C, vec);
   const int grid = ew_grid(total, vec * 4, threads);
-  if (vec == 4) bn_bwd_apply_kernel<4><<<grid, threads, 0, stream>>>(dz, mask, y, k1, k2, k3, dy, g_out, g_accumulate, total, C);
-  else if (vec == 2) bn_bwd_apply_kernel<2><<<grid, threads, 0, stream>>>(dz, mask, y, k1, k2, k3, dy, g_out, g_accumulate, total, C);
-  else bn_bwd_apply_kernel<1><<<grid, threads, 0, stream>>>(dz, mask, y, k1, k2, k3, dy, g_out, g_accumulate, total, C);
+  if (vec == 4) bn_bwd_apply_kernel<4><<<grid, threads, 0, stream>>>(dz, mask, y, mask_scale, mask_shift, k1, k2, k3, dy, g_out, g_accumulate, total, C);
+  else if (vec == 2) bn_bwd_apply_kernel<2><<<grid, threads, 0, stream>>>(dz, mask, y, mask_scale, mask_shift, k1, k2, k3, dy, g_out, g_accumulate, total, C);
+  else bn_bwd_apply_kernel<1><<<grid, threads, 0, stream>>>(dz, mask, y, mask_scale, mask_shift, k1, k2, k3, dy, g_out, g_accumulate, total, C);
   HCM_LAUNCH_CHECK("bn_bwd_apply");
   return HCM_OK;
 }

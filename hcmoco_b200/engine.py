@@ -1,0 +1,834 @@
+"""Host engine of the HCMoCo pre-train step: builds, once per (batch, resolution, model) shape, a static
+launch program over preallocated device buffers — forward, losses, backward, bank update, SGD — whose
+every arithmetic op is a C-ABI call into libhcmoco_sm100.so (include/hcmoco.h).  The program only
+enqueues kernels on the current stream, so it replays under a CUDA graph.
+
+What it restates (paths relative to pycontrast/ in the reference):
+  model      networks/build_backbone.py:186-303 (CMC3HRNetSGCNSingleHead), official_hrnet.py:32-454,
+             SGCN/sem_gcn.py:8-95, SGCN/sem_graph_conv.py:34-48
+  NCE        memory/mem_bank.py:157-205, learning/contrast_trainer.py:212-253
+  dense      learning/contrast_trainer.py:642-723     sparse  :744-828     SCL  :830-892
+  step       learning/contrast_trainer.py:532-640 (first stage), :894-1039 (second stage)
+  optimiser  main_contrast.py:78-81 (SGD momentum 0.9, wd 1e-4)
+
+Layout: activations channels-last fp32 [B,H,W,C]; conv weights in checkpoint layout (OIHW) inside one
+flat parameter buffer (+ flat gradient and momentum buffers of the same shape, so the optimiser and
+the gradient all-reduce are single launches).  A BatchNorm is never applied as a separate pass when
+its consumer is a convolution: the consumer applies scale/shift(+ReLU) while loading (`Act.scale`).
+"""
+from collections import OrderedDict
+
+import torch
+
+from . import layout as L
+
+BN2D_MOMENTUM = 0.01    # official_hrnet.py:22-23
+BN1D_MOMENTUM = 0.1     # nn.BatchNorm1d default (sem_gcn.py:13)
+BN_EPS = 1e-5
+
+
+class Act:
+    """Activation value = relu?(data * scale + shift); scale None -> value = data (materialised)."""
+    __slots__ = ("data", "B", "H", "W", "C", "scale", "shift", "relu", "grad", "grad_ready", "needs_grad", "spec",
+                 "consumers")
+
+    def __init__(self, data, B, H, W, C, scale=None, shift=None, relu=False, needs_grad=True):
+        self.data, self.B, self.H, self.W, self.C = data, B, H, W, C
+        self.scale, self.shift, self.relu = scale, shift, relu
+        self.grad, self.grad_ready, self.needs_grad = None, False, needs_grad
+        self.spec = None        # lazy acts: how the single consumer hands the gradient over
+        self.consumers = 0
+
+    @property
+    def P(self):
+        return self.B * self.H * self.W
+
+    @property
+    def lazy(self):
+        return self.scale is not None
+
+
+class ParamStore:
+    """Flat fp32 parameter / gradient / momentum buffers with per-key views in checkpoint layout."""
+
+    def __init__(self, K, keys):
+        self.keys = keys
+        self.K = K
+        off, self.off = 0, {}
+        for k, shp in keys.items():
+            if L.is_buffer(k):
+                continue
+            n = 1
+            for s in shp:
+                n *= s
+            self.off[k] = (off, n)
+            off += (n + 3) // 4 * 4
+        self.n = off
+        self.p = K.zeros(off)
+        self.g = K.zeros(off)
+        self.m = K.zeros(off)
+        self.buffers = OrderedDict()
+        for k, shp in keys.items():
+            if k.endswith("num_batches_tracked"):
+                self.buffers[k] = K.zeros((), dtype=torch.int64)
+            elif k.endswith("running_mean"):
+                self.buffers[k] = K.zeros(*shp)
+            elif k.endswith("running_var"):
+                self.buffers[k] = K.zeros(*shp) + 1.0
+
+    def view(self, flat, key):
+        o, n = self.off[key]
+        return flat[o:o + n]
+
+    def param(self, key):
+        return self.view(self.p, key)
+
+    def grad(self, key):
+        return self.view(self.g, key)
+
+    # ---- checkpoint layout <-> internal layout.  Only the 1x1 projection differs: its [128,Cm] matrix is
+    # stored as four per-branch column blocks, each contiguous [128,Cj] (see Engine._projection).
+    def _split_cols(self, key):
+        if key.startswith("encoder") and "_linear.weight" in key:
+            cm = self.keys[key][1]
+            for w, ch in L.WIDTHS.items():
+                if sum(ch) == cm:
+                    return ch
+        return None
+
+    def export(self, flat, key):
+        v = self.view(flat, key)
+        cols = self._split_cols(key)
+        if cols is None:
+            return v.reshape(self.keys[key]).clone()
+        parts, o = [], 0
+        for c in cols:
+            parts.append(v[o:o + 128 * c].reshape(128, c))
+            o += 128 * c
+        return torch.cat(parts, 1).reshape(self.keys[key]).clone()
+
+    def load(self, flat, key, t):
+        v = self.view(flat, key)
+        t = t.to(device=v.device, dtype=v.dtype)
+        cols = self._split_cols(key)
+        if cols is None:
+            v.copy_(t.reshape(-1))
+            return
+        t = t.reshape(128, -1)
+        o = c0 = 0
+        for c in cols:
+            v[o:o + 128 * c].copy_(t[:, c0:c0 + c].reshape(-1))
+            o += 128 * c
+            c0 += c
+
+    def state_dict(self, prefix=""):
+        out = OrderedDict()
+        for k in self.keys:
+            out[prefix + k] = self.buffers[k].clone() if L.is_buffer(k) else self.export(self.p, k)
+        return out
+
+    def load_state_dict(self, sd, strict=True):
+        missing = []
+        for k in self.keys:
+            src = sd.get(k, sd.get("module." + k))
+            if src is None:
+                missing.append(k)
+                continue
+            if L.is_buffer(k):
+                self.buffers[k].copy_(src.to(self.buffers[k].device))
+            else:
+                if tuple(src.shape) != tuple(self.keys[k]):
+                    raise ValueError("shape mismatch for %s: %s vs %s" % (k, tuple(src.shape), self.keys[k]))
+                self.load(self.p, k, src)
+        if strict and missing:
+            raise KeyError("missing keys: %s ..." % missing[:5])
+        return missing
+
+    def grads_dict(self):
+        return OrderedDict((k, self.export(self.g, k)) for k in self.keys if not L.is_buffer(k))
+
+
+class Plan:
+    """Recorded launch lists.  `f` appends a forward launch; ops register a backward *builder* that is
+    invoked in reverse op order by `finish()`, so that first-writer / accumulate flags of gradient
+    buffers are resolved statically."""
+
+    def __init__(self, K):
+        self.K = K
+        self.fwd, self.bwd, self._builders = [], [], []
+        self._cur = self.fwd
+
+    def f(self, fn, *args):
+        self.fwd.append((fn, args))
+
+    def b(self, fn, *args):
+        self.bwd.append((fn, args))
+
+    def on_backward(self, builder):
+        self._builders.append(builder)
+
+    def finish(self):
+        for bld in reversed(self._builders):
+            bld()
+        self._builders = []
+
+    def grad(self, act):
+        """Gradient buffer of a materialised act + whether the next writer must accumulate."""
+        if act.grad is None:
+            act.grad = self.K.empty(act.B, act.H, act.W, act.C)
+        acc = act.grad_ready
+        act.grad_ready = True
+        return act.grad, int(acc)
+
+    def zeroed_grad(self, act):
+        """Gradient buffer that scatter-style writers (atomics) can add into."""
+        if act.grad is None:
+            act.grad = self.K.empty(act.B, act.H, act.W, act.C)
+        if not act.grad_ready:
+            self.b(self.K.zero, act.grad, act.grad.numel() * act.grad.element_size())
+            act.grad_ready = True
+        return act.grad
+
+    @staticmethod
+    def run(prog):
+        for fn, args in prog:
+            fn(*args)
+
+
+class Engine:
+    def __init__(self, K, width=18, stage=1, skeleton="mpii", B=2, R=224, n_data=20000, nce_k=16384, nce_t=0.07,
+                 nce_m=0.5, temperature=0.07, num_samples=400, feat_dim=128, world_size=1, train=True):
+        assert feat_dim == 128, "the NCE / loss kernels are specialised for feat_dim=128"
+        assert R % 32 == 0, "HRNet needs the input side to be a multiple of 32"
+        assert B >= 2, "the reference collapses B=1 (mem_bank.py:39 out.squeeze())"
+        self.K, self.width, self.stage, self.skeleton = K, width, stage, skeleton
+        self.B, self.R, self.h = B, R, R // 4
+        self.J, rows, cols = L.graph_edges(skeleton)
+        self.nnz = len(rows)
+        self.n_data, self.K1, self.T_nce, self.m_nce = n_data, nce_k + 1, nce_t, nce_m
+        self.T, self.S = temperature, num_samples
+        self.world = world_size
+        self.ch = L.WIDTHS[width]
+        self.cm = sum(self.ch)
+        self.store = ParamStore(K, L.model_keys(width, stage, skeleton, feat_dim))
+        self.edge_rows = torch.tensor(rows, dtype=torch.int32, device=K.device)
+        self.edge_cols = torch.tensor(cols, dtype=torch.int32, device=K.device)
+        self.banks = None
+        self.first_step = True
+        self.built = False
+
+    # ------------------------------------------------------------------ memory bank (mem_bank.py:157-170)
+    def init_banks(self, banks=None, seed=0):
+        if banks is None:
+            g = torch.Generator().manual_seed(seed)
+            banks = [torch.nn.functional.normalize(torch.randn(self.n_data, 128, generator=g)) for _ in range(3)]
+        self.banks = [b.to(device=self.K.device, dtype=self.K.dtype).contiguous().clone() for b in banks]
+
+    # ------------------------------------------------------------------ plan construction
+    def build(self):
+        K, B, R, J = self.K, self.B, self.R, self.J
+        self.plan = p = Plan(K)
+        maxc = 4 * max(self.ch[-1], 256)
+        # shared scratch (single stream => sequential reuse is safe)
+        self.part = K.empty(2 * 4096 * 2 * 256)
+        self.k1, self.k2, self.k3 = K.empty(maxc), K.empty(maxc), K.empty(maxc)
+        # step inputs (static buffers; the caller copies each batch in)
+        self.x = K.zeros(B, 6, R, R)
+        self.skel = K.zeros(B, J, 2)
+        self.index = K.zeros(B, dtype=torch.int64)
+        self.joints_yx = K.zeros(B, J, 2)
+        self.joints_vis = K.zeros(B, J, dtype=torch.int32)
+        self.use_depth = K.zeros(B, dtype=torch.int64)
+        self.depth_mask = K.zeros(B, R, R)
+        self.nce_idx = K.zeros(B, self.K1, dtype=torch.int64)
+        self.dense_idx = K.zeros(B, self.S, dtype=torch.int64)
+        # model
+        xs = []
+        for m in range(2):
+            xin = K.empty(B, R, R, 3)
+            p.f(K.nchw_to_nhwc, self.x, xin, B, 6, R * R, 3 * m, 3)
+            xs.append(Act(xin, B, R, R, 3, needs_grad=False))
+        self.feat1 = self._hrnet("encoder1.", xs[0])
+        self.feat2 = self._hrnet("encoder2.", xs[1])
+        self.feat3 = self._sgcn("encoder3.", self.skel)
+        self.f = K.empty(B, 384)
+        self.df = K.zeros(B, 384)
+        self._head("head1.0", self._pool(self.feat1), self.cm, 0)
+        self._head("head2.0", self._pool(self.feat2), self.cm, 1)
+        self._head("head3.0", self._joint_mean(self.feat3), 128, 2)
+        if self.stage == 2:
+            self.lm1 = self._projection("encoder1_linear", self.feat1)
+            self.lm2 = self._projection("encoder2_linear", self.feat2)
+        self.n_model_fwd = len(p.fwd)
+        # losses (the builders registered here run first in the backward)
+        self.losses = K.zeros(16)     # 0-5 nce, 6-7 dense, 8-9 joint, 10 scl
+        self.accs = K.zeros(16)       # 0-5 nce, 6-7 dense, 8-9 joint
+        self._nce()
+        if self.stage == 2:
+            self._stage2_losses()
+        p.finish()
+        self.built = True
+        return self
+
+    # ---- conv + train-mode BN; output is lazy (raw conv output + per-channel affine)
+    def _conv_bn(self, x, ck, bk, stride, relu):
+        K, p, st = self.K, self.plan, self.store
+        cout, cin, ks, _ = st.keys[ck + ".weight"]
+        assert cin == x.C, (ck, cin, x.C)
+        B, H, W = x.B, x.H, x.W
+        pad = (ks - 1) // 2
+        Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
+        P = B * Ho * Wo
+        y = K.empty(B, Ho, Wo, cout)
+        w = st.param(ck + ".weight")
+        rows = K.conv2d_stat_rows(B, H, W, cin, cout, ks, stride)
+        assert rows * 2 * cout <= self.part.numel()
+        scale, shift, mean, invstd = K.empty(cout), K.empty(cout), K.empty(cout), K.empty(cout)
+        bf = st.buffers
+        x.consumers += 1
+        p.f(K.conv2d_fwd, x.data, w, None, y, B, H, W, cin, cout, ks, stride, x.scale, x.shift, int(x.relu), self.part)
+        p.f(K.bn_finalize, self.part, rows, cout, P, st.param(bk + ".weight"), st.param(bk + ".bias"),
+            bf[bk + ".running_mean"], bf[bk + ".running_var"], bf[bk + ".num_batches_tracked"], BN2D_MOMENTUM, BN_EPS,
+            scale, shift, mean, invstd)
+        out = Act(y, B, Ho, Wo, cout, scale, shift, relu)
+
+        def backward():
+            # gradient wrt the lazy value arrives either in out.grad (consumer was a conv: in place) or via out.spec
+            if out.spec is None:
+                assert out.grad is not None, "lazy act without consumer: " + ck
+                spec = dict(dz=out.grad, mask=None, recompute=relu, dy=out.grad, g_out=None, g_acc=0)
+            else:
+                spec = out.spec
+            msc, msh = (scale, shift) if spec["recompute"] else (None, None)
+            nparts = K.colstat_rows(P, cout)
+            p.b(K.bn_bwd_reduce, spec["dz"], spec["mask"], msc, msh, y, mean, invstd, P, cout, self.part)
+            p.b(K.bn_bwd_finalize, self.part, nparts, cout, P, st.param(bk + ".weight"), mean, invstd,
+                st.grad(bk + ".weight"), st.grad(bk + ".bias"), self.k1, self.k2, self.k3)
+            p.b(K.bn_bwd_apply, spec["dz"], spec["mask"], msc, msh, y, self.k1, self.k2, self.k3, spec["dy"],
+                spec["g_out"], spec["g_acc"], P, cout)
+            dy = spec["dy"]
+            p.b(K.conv2d_wgrad, x.data, dy, st.grad(ck + ".weight"), B, H, W, cin, cout, ks, stride, x.scale, x.shift,
+                int(x.relu))
+            if x.needs_grad:
+                if x.lazy:
+                    assert x.consumers == 1 and x.grad is None
+                    x.grad = K.empty(B, H, W, cin)
+                    p.b(K.conv2d_dgrad, dy, w, x.grad, B, H, W, cin, cout, ks, stride, 0)
+                else:
+                    gx, acc = p.grad(x)
+                    p.b(K.conv2d_dgrad, dy, w, gx, B, H, W, cin, cout, ks, stride, acc)
+
+        p.on_backward(backward)
+        return out
+
+    # ---- out = act(bn(y) [+ residual]) as a materialised tensor
+    def _materialize(self, a, res=None, relu=None):
+        K, p = self.K, self.plan
+        relu = a.relu if relu is None else relu
+        out = Act(K.empty(a.B, a.H, a.W, a.C), a.B, a.H, a.W, a.C)
+        a.consumers += 1
+        if res is not None:
+            res.consumers += 1
+        p.f(K.bn_apply, a.data, a.scale, a.shift, None if res is None else res.data, None if res is None else res.scale,
+            None if res is None else res.shift, int(relu), out.data, a.P, a.C)
+
+        def backward():
+            assert out.grad is not None, "materialised act without gradient"
+            mask = out.data if relu else None
+            if res is not None and res.lazy:      # projection shortcut (Bottleneck downsample): needs its own dy
+                res.grad = K.empty(a.B, a.H, a.W, a.C)
+                res.spec = dict(dz=out.grad, mask=mask, recompute=False, dy=res.grad, g_out=None, g_acc=0)
+                # the shortcut's producer runs *after* the main branch in the backward (it was built earlier),
+                # so the main branch must not overwrite out.grad in place
+                a.grad = K.empty(a.B, a.H, a.W, a.C)
+                a.spec = dict(dz=out.grad, mask=mask, recompute=False, dy=a.grad, g_out=None, g_acc=0)
+                return
+            g_out, g_acc = (None, 0)
+            if res is not None and res.needs_grad:
+                g_out, g_acc = p.grad(res)
+            a.spec = dict(dz=out.grad, mask=mask, recompute=False, dy=out.grad, g_out=g_out, g_acc=g_acc)
+
+        p.on_backward(backward)
+        return out
+
+    def _basic_block(self, x, q):          # official_hrnet.py:32-61
+        y = self._conv_bn(x, q + "conv1", q + "bn1", 1, True)
+        y = self._conv_bn(y, q + "conv2", q + "bn2", 1, False)
+        return self._materialize(y, res=x, relu=True)
+
+    def _bottleneck(self, x, q, down):     # official_hrnet.py:64-102
+        r = self._conv_bn(x, q + "downsample.0", q + "downsample.1", 1, False) if down else x
+        y = self._conv_bn(x, q + "conv1", q + "bn1", 1, True)
+        y = self._conv_bn(y, q + "conv2", q + "bn2", 1, True)
+        y = self._conv_bn(y, q + "conv3", q + "bn3", 1, False)
+        return self._materialize(y, res=r, relu=True)
+
+    # ---- HR-module fuse: out_i = relu(sum_j T_ij(x_j))   (official_hrnet.py:176-220, 232-247)
+    def _fuse(self, xs, mp, i):
+        K, p = self.K, self.plan
+        n = len(xs)
+        xi = xs[i]
+        terms = []            # (act, log2 factor, kind)
+        for j in range(n):
+            q = "%sfuse_layers.%d.%d." % (mp, i, j)
+            if j == i:
+                terms.append((xs[j], 0, "id"))
+            elif j > i:
+                terms.append((self._conv_bn(xs[j], q + "0", q + "1", 1, False), j - i, "up"))
+            else:
+                t = xs[j]
+                for hop in range(i - j):
+                    t = self._conv_bn(t, "%s%d.0" % (q, hop), "%s%d.1" % (q, hop), 2, hop != i - j - 1)
+                terms.append((t, 0, "down"))
+        out = Act(K.empty(xi.B, xi.H, xi.W, xi.C), xi.B, xi.H, xi.W, xi.C)
+        for t, _, _ in terms:
+            t.consumers += 1
+        log2f = torch.tensor([t[1] for t in terms], dtype=torch.int32)
+        p.f(K.fuse_sum, n, [t[0].data for t in terms], [t[0].scale for t in terms], [t[0].shift for t in terms], log2f,
+            None, 1, out.data, xi.B, xi.H, xi.W, xi.C)
+
+        def backward():
+            assert out.grad is not None
+            G = out.grad
+            total = G.numel()
+            p.b(K.relu_bwd, G, out.data, G, 0, total)          # G <- G * [out > 0], in place
+            for t, k, kind in terms:
+                if kind == "id":
+                    gx, acc = p.grad(t)
+                    if acc:
+                        p.b(K.axpy, gx, G, 1.0, total)
+                    else:
+                        p.b(K.relu_bwd, G, out.data, gx, 0, total)   # masked copy (idempotent)
+                elif kind == "down":
+                    t.grad = K.empty(t.B, t.H, t.W, t.C)
+                    t.spec = dict(dz=G, mask=None, recompute=False, dy=t.grad, g_out=None, g_acc=0)
+                else:
+                    t.grad = K.empty(t.B, t.H, t.W, t.C)
+                    p.b(K.upsample_adjoint, G, t.grad, 0, xi.B, xi.H, xi.W, xi.C, k)
+                    t.spec = dict(dz=t.grad, mask=None, recompute=False, dy=t.grad, g_out=None, g_acc=0)
+
+        p.on_backward(backward)
+        return out
+
+    def _hr_module(self, xs, mp):
+        xs = list(xs)
+        for i in range(len(xs)):
+            for blk in range(4):
+                xs[i] = self._basic_block(xs[i], "%sbranches.%d.%d." % (mp, i, blk))
+        return [self._fuse(xs, mp, i) for i in range(len(xs))]
+
+    def _hrnet(self, pre, x):              # official_hrnet.py:411-454
+        st = self.store
+        y = self._conv_bn(x, pre + "conv1", pre + "bn1", 2, True)
+        y = self._conv_bn(y, pre + "conv2", pre + "bn2", 2, True)
+        x = self._materialize(y)
+        for blk in range(4):
+            x = self._bottleneck(x, "%slayer1.%d." % (pre, blk), blk == 0)
+        ys = [x]
+        for s, (nmod, nbr) in enumerate(L.STAGES):
+            t = "%stransition%d." % (pre, s + 1)
+            xs = []
+            for i in range(nbr):
+                if i < len(ys):
+                    if ("%s%d.0.weight" % (t, i)) in st.keys:
+                        xs.append(self._materialize(self._conv_bn(ys[i], "%s%d.0" % (t, i), "%s%d.1" % (t, i), 1, True)))
+                    else:
+                        xs.append(ys[i])
+                else:
+                    a = ys[-1]
+                    for j in range(i + 1 - len(ys)):
+                        a = self._conv_bn(a, "%s%d.%d.0" % (t, i, j), "%s%d.%d.1" % (t, i, j), 2, True)
+                    xs.append(self._materialize(a))
+            for m in range(nmod):
+                xs = self._hr_module(xs, "%sstage%d.%d." % (pre, s + 2, m))
+            ys = xs
+        return ys
+
+    # ---- SemGCN (sem_gcn.py:60-95; sem_graph_conv.py:34-48): x [B*J, Cin] rows
+    def _gconv(self, x, xg_slot, q, cin, cout, bn):
+        """x: tensor [B,J,cin]; xg_slot: dict with 'grad' tensor or None (input has no grad), 'ready' flag.
+        Returns (value tensor [B,J,cout] post BN/ReLU if bn else raw, slot)."""
+        K, p, st, B, J = self.K, self.plan, self.store, self.B, self.J
+        A = K.empty(J, J)
+        xa = K.empty(B, J, 2 * cin)
+        y = K.empty(B, J, cout)
+        W, e, bias = st.param(q + ".gconv.W" if bn else q + ".W"), st.param(q + ".gconv.e" if bn else q + ".e"), \
+            st.param(q + ".gconv.bias" if bn else q + ".bias")
+        gk = (q + ".gconv") if bn else q
+        M = B * J
+        p.f(K.sgcn_adj, e, self.edge_rows, self.edge_cols, self.nnz, J, A)
+        p.f(K.sgcn_aggregate, x, A, B, J, cin, xa)
+        p.f(K.gemm, xa, W, bias, y, 1, M, cout, 2 * cin, 2 * cin, 1, cout, 1, cout, 0, 0, 0, 1.0, 0)
+        slot = dict(grad=None, ready=False)
+        if bn:
+            bk = q + ".bn"
+            scale, shift, mean, invstd = K.empty(cout), K.empty(cout), K.empty(cout), K.empty(cout)
+            out = K.empty(B, J, cout)
+            nparts = K.colstat_rows(M, cout)
+            bf = st.buffers
+            p.f(K.bn_stats, y, M, cout, self.part)
+            p.f(K.bn_finalize, self.part, nparts, cout, M, st.param(bk + ".weight"), st.param(bk + ".bias"),
+                bf[bk + ".running_mean"], bf[bk + ".running_var"], bf[bk + ".num_batches_tracked"], BN1D_MOMENTUM,
+                BN_EPS, scale, shift, mean, invstd)
+            p.f(K.bn_apply, y, scale, shift, None, None, None, 1, out, M, cout)
+        else:
+            out = y
+
+        def backward():
+            G = slot["grad"]
+            assert G is not None and slot["ready"], "gconv output without gradient: " + q
+            if bn:
+                p.b(K.bn_bwd_reduce, G, out, None, None, y, mean, invstd, M, cout, self.part)
+                p.b(K.bn_bwd_finalize, self.part, nparts, cout, M, st.param(bk + ".weight"), mean, invstd,
+                    st.grad(bk + ".weight"), st.grad(bk + ".bias"), self.k1, self.k2, self.k3)
+                p.b(K.bn_bwd_apply, G, out, None, None, y, self.k1, self.k2, self.k3, G, None, 0, M, cout)
+            dy = G
+            # bias, W ([2*cin, cout] stacked), aggregated input
+            p.b(K.colsum_small, dy, M, cout, cout, st.grad(gk + ".bias"), 0)
+            # dW[k][n] = sum_m xa[m][k] * dy[m][n]
+            p.b(K.gemm, xa, dy, None, st.grad(gk + ".W"), 1, 2 * cin, cout, M, 1, 2 * cin, cout, 1, cout, 0, 0, 0, 1.0, 0)
+            dxa = K.empty(B, J, 2 * cin)
+            # dxa[m][k] = sum_n dy[m][n] * W[k][n]
+            p.b(K.gemm, dy, W, None, dxa, 1, M, 2 * cin, cout, cout, 1, 1, cout, 2 * cin, 0, 0, 0, 1.0, 0)
+            dA = K.empty(J, J)
+            if xg_slot is not None:
+                if xg_slot["grad"] is None:
+                    xg_slot["grad"] = K.empty(B, J, cin)
+                acc = int(xg_slot["ready"])
+                xg_slot["ready"] = True
+                p.b(K.sgcn_aggregate_bwd, dxa, x, A, B, J, cin, xg_slot["grad"], acc, dA)
+            else:
+                p.b(K.sgcn_aggregate_bwd, dxa, x, A, B, J, cin, None, 0, dA)
+            p.b(K.sgcn_adj_bwd, A, dA, self.edge_rows, self.edge_cols, self.nnz, J, st.grad(gk + ".e"), 0)
+
+        p.on_backward(backward)
+        return out, slot
+
+    def _sgcn(self, pre, s):
+        K, p, B, J = self.K, self.plan, self.B, self.J
+        x, xs = self._gconv(s, None, pre + "gconv_input.0", 2, 128, True)
+        for layer in range(4):
+            q = "%sgconv_layers.%d." % (pre, layer)
+            y1, s1 = self._gconv(x, xs, q + "gconv1", 128, 128, True)
+            y2, s2 = self._gconv(y1, s1, q + "gconv2", 128, 128, True)
+            out = K.empty(B, J, 128)
+            outs = dict(grad=None, ready=False)
+            n = B * J * 128
+            p.f(K.bn_apply, x, None, None, y2, None, None, 0, out, B * J, 128)       # out = x + y2
+
+            def backward(xs=xs, s2=s2, outs=outs, n=n):
+                G = outs["grad"]
+                assert G is not None and outs["ready"]
+                s2["grad"], s2["ready"] = G, True                 # d y2 = G (shared, gconv2's BN bwd runs in place last)
+                if xs["grad"] is None:
+                    xs["grad"] = K.empty(B, J, 128)
+                if xs["ready"]:
+                    p.b(K.axpy, xs["grad"], G, 1.0, n)
+                else:
+                    p.b(K.bn_apply, G, None, None, None, None, None, 0, xs["grad"], B * J, 128)   # copy
+                    xs["ready"] = True
+
+            p.on_backward(backward)
+            x, xs = out, outs
+        y, ys = self._gconv(x, xs, pre + "gconv_output", 128, 128, False)
+        self.feat3_slot = ys
+        return y
+
+    def _slot_grad(self, slot, shape):
+        if slot["grad"] is None:
+            slot["grad"] = self.K.empty(*shape)
+        acc = int(slot["ready"])
+        slot["ready"] = True
+        return slot["grad"], acc
+
+    # ---- global average pool of the four branches, concatenated (build_backbone.py:267-278)
+    def _pool(self, feats):
+        K, p, B = self.K, self.plan, self.B
+        a = K.empty(B, self.cm)
+        da = K.empty(B, self.cm)
+        off = 0
+        offs = []
+        for ft in feats:
+            ft.consumers += 1
+            p.f(K.avgpool, ft.data, a, B, ft.H * ft.W, ft.C, self.cm, off)
+            offs.append(off)
+            off += ft.C
+
+        def backward():
+            for ft, o in zip(feats, offs):
+                g, acc = p.grad(ft)
+                p.b(K.avgpool_bwd, da, g, acc, B, ft.H * ft.W, ft.C, self.cm, o)
+
+        p.on_backward(backward)
+        return a, da
+
+    def _joint_mean(self, feat3):          # build_backbone.py:279
+        K, p, B, J = self.K, self.plan, self.B, self.J
+        a, da = K.empty(B, 128), K.empty(B, 128)
+        p.f(K.joint_mean, feat3, B, J, 128, a)
+
+        def backward():
+            g, acc = self._slot_grad(self.feat3_slot, (B, J, 128))
+            p.b(K.joint_mean_bwd, da, B, J, 128, g, acc)
+
+        p.on_backward(backward)
+        return a, da
+
+    # ---- Linear + L2 head (build_backbone.py:226-241, networks/util.py:74-81) writing f[:, 128*m : 128*(m+1)]
+    def _head(self, key, pooled, cin, m):
+        K, p, st, B = self.K, self.plan, self.store, self.B
+        a, da = pooled
+        W, bias = st.param(key + ".weight"), st.param(key + ".bias")
+        lin, inv, dlin = K.empty(B, 128), K.empty(B), K.empty(B, 128)
+        fm = self.f[:, 128 * m:128 * (m + 1)]
+        dfm = self.df[:, 128 * m:128 * (m + 1)]
+        p.f(K.gemm, a, W, bias, lin, 1, B, 128, cin, cin, 1, 1, cin, 128, 0, 0, 0, 1.0, 0)
+        p.f(K.gather_l2norm, lin, 128, None, 0, 1, B, 128, fm, 384, inv)
+
+        def backward():
+            p.b(K.gather_l2norm_bwd, dfm, 384, fm, 384, inv, None, 0, 1, B, 128, dlin, 128, 0)
+            p.b(K.colsum_small, dlin, B, 128, 128, st.grad(key + ".bias"), 0)
+            # dW[n][k] = sum_b dlin[b][n] * a[b][k]
+            p.b(K.gemm, dlin, a, None, st.grad(key + ".weight"), 1, 128, cin, B, 1, 128, cin, 1, cin, 0, 0, 0, 1.0, 0)
+            # da[b][k] = sum_n dlin[b][n] * W[n][k]
+            p.b(K.gemm, dlin, W, None, da, 1, B, cin, 128, 128, 1, cin, 1, cin, 0, 0, 0, 1.0, 0)
+
+        p.on_backward(backward)
+
+    # ---- encoder{1,2}_linear over the bilinear merge of the four branches (build_backbone.py:247-254, 289-294).
+    # A 1x1 convolution commutes with bilinear interpolation (the interpolation weights sum to one), so each
+    # branch is projected at its own resolution (K = C_j) and the four 128-channel results are upsampled and
+    # summed by fuse_sum: the [B,Cm,h,h] merged map is never materialised.
+    def _projection(self, key, feats):
+        K, p, st, B, h = self.K, self.plan, self.store, self.B, self.h
+        wflat, bias = st.param(key + ".weight"), st.param(key + ".bias")
+        gflat = st.grad(key + ".weight")
+        ws, gs, ys, o = [], [], [], 0
+        for j, ft in enumerate(feats):
+            n = 128 * ft.C
+            ws.append(wflat[o:o + n])
+            gs.append(gflat[o:o + n])
+            o += n
+            ft.consumers += 1
+            y = K.empty(B, ft.H, ft.W, 128)
+            p.f(K.conv2d_fwd, ft.data, ws[j], None, y, B, ft.H, ft.W, ft.C, 128, 1, 1, None, None, 0, None)
+            ys.append(y)
+        out = Act(K.empty(B, h, h, 128), B, h, h, 128)
+        log2f = torch.tensor([0, 1, 2, 3], dtype=torch.int32)
+        p.f(K.fuse_sum, 4, ys, None, None, log2f, bias, 0, out.data, B, h, h, 128)
+
+        def backward():
+            G = out.grad
+            assert G is not None and out.grad_ready
+            P0 = B * h * h
+            nparts = K.colstat_rows(P0, 128)
+            p.b(K.bn_stats, G, P0, 128, self.part)
+            p.b(K.colsum_finalize, self.part, nparts, 128, st.grad(key + ".bias"), 0)
+            for j, ft in enumerate(feats):
+                if j == 0:
+                    Gj = G
+                else:
+                    Gj = K.empty(B, ft.H, ft.W, 128)
+                    p.b(K.upsample_adjoint, G, Gj, 0, B, h, h, 128, j)
+                p.b(K.conv2d_wgrad, ft.data, Gj, gs[j], B, ft.H, ft.W, ft.C, 128, 1, 1, None, None, 0)
+                gx, acc = p.grad(ft)
+                p.b(K.conv2d_dgrad, Gj, ws[j], gx, B, ft.H, ft.W, ft.C, 128, 1, 1, acc)
+
+        p.on_backward(backward)
+        return out
+
+    # ---- sample-level memory-bank NCE (mem_bank.py:172-205; contrast_trainer.py:212-253)
+    def _nce(self):
+        K, p, B, K1 = self.K, self.plan, self.B, self.K1
+        self.logits = K.empty(6, B, K1)
+        lse, l0, hit, coef = K.empty(6, B), K.empty(6, B), K.empty(6, B), K.empty(6, B)
+        f = self.f
+        x1, x2, x3 = f[:, 0:128], f[:, 128:256], f[:, 256:384]
+        self._nce_args = (x1, x2, x3)
+
+        def fwd_logits():
+            b = self.banks
+            K.nce_logits(b[0], b[1], b[2], x1, x2, x3, 384, self.nce_idx, B, K1, 128, self.T_nce, self.logits)
+
+        def bwd():
+            b = self.banks
+            K.nce_bwd(b[0], b[1], b[2], x1, x2, x3, 384, self.nce_idx, B, K1, 128, self.T_nce, self.logits, lse, coef,
+                      1.0, self.df, 384)
+
+        p.f(fwd_logits)
+        p.f(K.nce_loss, self.logits, B, K1, self.use_depth, None, lse, l0, hit, coef, self.losses[0:6], self.accs[0:6])
+
+        def backward():
+            p.b(K.zero, self.df, self.df.numel() * self.df.element_size())
+            p.b(bwd)
+
+        p.on_backward(backward)
+
+    # ---- dense intra-sample, sparse joint<->pixel and cross-subject SCL (contrast_trainer.py:642-892)
+    def _stage2_losses(self):
+        K, p, B, J, h, S, T = self.K, self.plan, self.B, self.J, self.h, self.S, self.T
+        G1, G2 = self.lm1, self.lm2
+        HW = h * h
+        G1.consumers += 3
+        G2.consumers += 3
+        # --- dense
+        kept = K.empty(B)
+        A, D = K.empty(B * S, 128), K.empty(B * S, 128)
+        inv_a, inv_d = K.empty(B * S), K.empty(B * S)
+        Ld = K.empty(B, S, S)
+        stat = K.empty(B, 2, S, 4)
+        fin_d = K.zeros(8)
+        p.f(K.dense_kept, self.depth_mask, B, self.R, h, kept)
+        p.f(K.gather_l2norm, G1.data, 0, self.dense_idx, HW, S, B * S, 128, A, 128, inv_a)
+        p.f(K.gather_l2norm, G2.data, 0, self.dense_idx, HW, S, B * S, 128, D, 128, inv_d)
+        # L[b][i][j] = <d_i, a_j>/T
+        p.f(K.gemm, D, A, None, Ld, B, S, S, 128, 128, 1, 1, 128, S, S * 128, S * 128, S * S, 1.0 / T, 0)
+        p.f(K.dense_stats, Ld, self.dense_idx, kept, self.use_depth, B, S, h, stat, fin_d)
+        p.f(K.bn_apply, fin_d, None, None, None, None, None, 0, self.losses[6:8], 1, 2)
+        p.f(K.bn_apply, fin_d[2:4], None, None, None, None, None, 0, self.accs[6:8], 1, 2)
+        # --- joints: F rows [0,BJ) rgb pixels, [BJ,2BJ) depth pixels (also the SCL feature matrix)
+        N = 2 * B * J
+        pixj = K.zeros(B, J, dtype=torch.int64)
+        Fm, inv_f, dF = K.empty(N, 128), K.empty(N), K.empty(N, 128)
+        Sk, inv_s, dSk = K.empty(B * J, 128), K.empty(B * J), K.empty(B * J, 128)
+        Lr, Ldj = K.empty(B, J, J), K.empty(B, J, J)
+        rs, lsej, fin_j = K.empty(B, 2, 3), K.empty(B, 2, J), K.zeros(8)
+        Fa, Fd = Fm[:B * J], Fm[B * J:]
+        dFa, dFd = dF[:B * J], dF[B * J:]
+        p.f(K.joint_pixel_index, self.joints_yx, B * J, h, pixj)
+        p.f(K.gather_l2norm, G1.data, 0, pixj, HW, J, B * J, 128, Fa, 128, inv_f[:B * J])
+        p.f(K.gather_l2norm, G2.data, 0, pixj, HW, J, B * J, 128, Fd, 128, inv_f[B * J:])
+        p.f(K.gather_l2norm, self.feat3, 128, None, 0, 1, B * J, 128, Sk, 128, inv_s)
+        # Lr[b][k][j] = <s_k, a_j>/T
+        p.f(K.gemm, Sk, Fa, None, Lr, B, J, J, 128, 128, 1, 1, 128, J, J * 128, J * 128, J * J, 1.0 / T, 0)
+        p.f(K.gemm, Sk, Fd, None, Ldj, B, J, J, 128, 128, 1, 1, 128, J, J * 128, J * 128, J * J, 1.0 / T, 0)
+        p.f(K.joint_stats, Lr, Ldj, self.joints_vis, self.use_depth, B, J, rs, lsej, fin_j)
+        p.f(K.bn_apply, fin_j, None, None, None, None, None, 0, self.losses[8:10], 1, 2)
+        p.f(K.bn_apply, fin_j[2:4], None, None, None, None, None, 0, self.accs[8:10], 1, 2)
+        # --- SCL
+        Z = K.empty(N, N)
+        rowstat, fin_s = K.empty(N, 3), K.zeros(4)
+        p.f(K.gemm, Fm, Fm, None, Z, 1, N, N, 128, 128, 1, 1, 128, N, 0, 0, 0, 1.0 / T, 0)
+        p.f(K.scl_stats, Z, B, J, None, self.use_depth, rowstat, fin_s)
+        p.f(K.bn_apply, fin_s, None, None, None, None, None, 0, self.losses[10:11], 1, 1)
+        self.stage2_debug = dict(Ld=Ld, Lr=Lr, Ldj=Ldj, Z=Z, fin_d=fin_d, fin_j=fin_j, fin_s=fin_s, kept=kept, pixj=pixj)
+
+        def backward():
+            iT = 1.0 / T
+            g1, g2 = p.zeroed_grad(G1), p.zeroed_grad(G2)
+            # joints: logits -> gradients in place; dF (rgb | depth rows), dSk
+            p.b(K.joint_grad, Lr, Ldj, self.joints_vis, self.use_depth, lsej, fin_j, B, J, 1.0)
+            # dSk[b][k][:] = iT * (sum_j dLr[k][j] a_j + sum_j dLd[k][j] d_j)
+            p.b(K.gemm, Lr, Fa, None, dSk, B, J, 128, J, J, 1, 128, 1, 128, J * J, J * 128, J * 128, iT, 0)
+            p.b(K.gemm, Ldj, Fd, None, dSk, B, J, 128, J, J, 1, 128, 1, 128, J * J, J * 128, J * 128, iT, 1)
+            # dFa[b][j][:] = iT * sum_k dLr[k][j] s_k
+            p.b(K.gemm, Lr, Sk, None, dFa, B, J, 128, J, 1, J, 128, 1, 128, J * J, J * 128, J * 128, iT, 0)
+            p.b(K.gemm, Ldj, Sk, None, dFd, B, J, 128, J, 1, J, 128, 1, 128, J * J, J * 128, J * 128, iT, 0)
+            # SCL: dF += iT * (dZ + dZ^T) F
+            p.b(K.scl_grad, Z, B, J, None, self.use_depth, rowstat, fin_s, 1.0)
+            p.b(K.gemm, Z, Fm, None, dF, 1, N, 128, N, N, 1, 128, 1, 128, 0, 0, 0, iT, 1)
+            p.b(K.gemm, Z, Fm, None, dF, 1, N, 128, N, 1, N, 128, 1, 128, 0, 0, 0, iT, 1)
+            p.b(K.gather_l2norm_bwd, dFa, 128, Fa, 128, inv_f[:B * J], pixj, HW, J, B * J, 128, g1, 0, 1)
+            p.b(K.gather_l2norm_bwd, dFd, 128, Fd, 128, inv_f[B * J:], pixj, HW, J, B * J, 128, g2, 0, 1)
+            gs, acc = self._slot_grad(self.feat3_slot, (B, J, 128))
+            p.b(K.gather_l2norm_bwd, dSk, 128, Sk, 128, inv_s, None, 0, 1, B * J, 128, gs, 128, acc)
+            # dense: dL in place; dD = iT * dL A ; dA = iT * dL^T D
+            dA, dD = K.empty(B * S, 128), K.empty(B * S, 128)
+            p.b(K.dense_grad, Ld, self.dense_idx, stat, kept, fin_d, B, S, h, 1.0)
+            p.b(K.gemm, Ld, A, None, dD, B, S, 128, S, S, 1, 128, 1, 128, S * S, S * 128, S * 128, iT, 0)
+            p.b(K.gemm, Ld, D, None, dA, B, S, 128, S, 1, S, 128, 1, 128, S * S, S * 128, S * 128, iT, 0)
+            p.b(K.gather_l2norm_bwd, dA, 128, A, 128, inv_a, self.dense_idx, HW, S, B * S, 128, g1, 0, 1)
+            p.b(K.gather_l2norm_bwd, dD, 128, D, 128, inv_d, self.dense_idx, HW, S, B * S, 128, g2, 0, 1)
+
+        p.on_backward(backward)
+
+    # ------------------------------------------------------------------ running
+    def set_batch(self, batch, nce_idx, dense_idx=None):
+        """batch: the reference's DataLoader tuple (see hcmoco_b200/synthetic.py) or a dict with the same fields."""
+        if not isinstance(batch, dict):
+            batch = dict(x=batch[0], index=batch[1], skeleton=batch[2], joints_yx=batch[4], joints_vis=batch[5],
+                         use_depth=batch[6], depth_mask=batch[7])
+        self.x.copy_(batch["x"], non_blocking=True)
+        self.index.copy_(batch["index"], non_blocking=True)
+        self.skel.copy_(batch["skeleton"], non_blocking=True)
+        self.joints_yx.copy_(batch["joints_yx"], non_blocking=True)
+        self.joints_vis.copy_(batch["joints_vis"], non_blocking=True)
+        self.use_depth.copy_(batch["use_depth"], non_blocking=True)
+        self.depth_mask.copy_(batch["depth_mask"], non_blocking=True)
+        self.nce_idx.copy_(nce_idx, non_blocking=True)
+        if dense_idx is not None:
+            self.dense_idx.copy_(dense_idx, non_blocking=True)
+
+    def forward(self):
+        Plan.run(self.plan.fwd)
+
+    def backward(self):
+        self.K.zero(self.store.g, self.store.n * self.store.g.element_size())
+        Plan.run(self.plan.bwd)
+
+    def update_banks(self, all_f=None, all_index=None):
+        """mem_bank.py:195-203 with the all-gathered embeddings (contrast_trainer.py:578-579)."""
+        f = self.f if all_f is None else all_f
+        y = self.index if all_index is None else all_index
+        N = f.shape[0]
+        for m in range(3):
+            self.K.bank_update(self.banks[m], f[:, 128 * m:128 * (m + 1)], 384, y, N, 128, self.m_nce)
+
+    def sgd(self, lr=0.03, momentum=0.9, wd=1e-4, gscale=1.0):
+        # the momentum buffer starts at zero, so torch.optim.SGD's "first step: buf = grad" is the same update
+        st = self.store
+        self.K.sgd_step(st.p, st.g, st.m, st.n, lr, momentum, wd, 0, gscale)
+        self.first_step = False
+
+    def step(self, lr=0.03, momentum=0.9, wd=1e-4):
+        """Single-rank step: forward, losses, backward, bank update, SGD."""
+        self.forward()
+        self.backward()
+        self.update_banks()
+        self.sgd(lr, momentum, wd)
+
+    # ---- CUDA graph: forward + losses + backward are one graph launch (every buffer is static)
+    def capture(self):
+        saved = [(b, b.clone()) for b in self.store.buffers.values()]
+        self.forward()                     # warm-up outside capture (module loading), then undo its BN side effects
+        self.backward()
+        for b, c in saved:
+            b.copy_(c)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.forward()
+            self.backward()
+        for b, c in saved:
+            b.copy_(c)
+        return self
+
+    def step_graph(self, lr=0.03, momentum=0.9, wd=1e-4):
+        self.graph.replay()
+        self.update_banks()
+        self.sgd(lr, momentum, wd)
+
+    @property
+    def launches_per_step(self):
+        """C-ABI calls in one step (each enqueues at least one kernel)."""
+        return len(self.plan.fwd) + len(self.plan.bwd) + 1 + 3 + 1
+
+    def total_loss(self):
+        n = 11 if self.stage == 2 else 6
+        return self.losses[:n].sum()
+
+    def results(self):
+        """Host copy of the step's losses and accuracies (one D2H read)."""
+        la = torch.cat([self.losses, self.accs]).cpu()
+        ls, ac = la[:16], la[16:]
+        out = dict(nce_losses=ls[0:6], nce_accs=ac[0:6])
+        if self.stage == 2:
+            out.update(dense_losses=ls[6:8], dense_accs=ac[6:8], joint_losses=ls[8:10], joint_accs=ac[8:10],
+                       scl_loss=ls[10])
+        out["loss"] = ls[:11 if self.stage == 2 else 6].sum()
+        return out
+
+    # NCHW views for the drop-in surface / tests
+    @staticmethod
+    def nchw(act):
+        return act.data.permute(0, 3, 1, 2)

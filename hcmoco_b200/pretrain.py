@@ -1,0 +1,159 @@
+"""One data-parallel pre-train step on top of the engine: random draws, CUDA-graph replay of
+forward+losses+backward, embedding all-gather -> memory-bank update, gradient all-reduce, fused SGD.
+
+Follows learning/contrast_trainer.py:532-640 (`_train_mem_skeleton3d`) and :894-1039
+(`_train_bank_joints_pri3d_cmc3`); collectives as in SURVEY.md §8(e): NCCL all-reduce of the flat
+gradient buffer (one message instead of DDP's buckets), all-gather of [B,384] embeddings + [B] indices
+so that every rank applies the identical bank update (contrast_trainer.py:578-579, mem_bank.py:195-199).
+"""
+import math
+
+import torch
+
+from . import layout as L
+from .engine import Engine, Plan
+
+
+def init_parameters(store, seed=0):
+    """The reference's initialisers: HRNet convs N(0, 0.001^2), BN gamma 1 / beta 0
+    (official_hrnet.py:456-463); nn.Linear / nn.Conv2d defaults for the heads and the 1x1 projections;
+    SemGraphConv: xavier_uniform(gain 1.414) W, e = 1, bias U(+-1/sqrt(out)) (sem_graph_conv.py:19-30)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in store.keys.items():
+        if L.is_buffer(k):
+            continue
+        if k.endswith(".W"):
+            bound = 1.414 * math.sqrt(6.0 / (shp[1] + shp[2]))
+            t = (torch.rand(shp, generator=g) * 2 - 1) * bound
+        elif k.endswith(".e"):
+            t = torch.ones(shp)
+        elif len(shp) == 4 and "_linear" in k:
+            t = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(shp[1])
+        elif len(shp) == 4:
+            t = 0.001 * torch.randn(shp, generator=g)
+        elif len(shp) == 2:
+            t = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(shp[1])
+        elif k.endswith(".weight"):                    # BatchNorm gamma
+            t = torch.ones(shp)
+        elif ".gconv" in k or k.startswith("head") or "_linear" in k:      # linear / gconv / projection biases
+            fan = {"head1": store.keys.get("head1.0.weight", (0, 1))[1], "head2": store.keys.get("head2.0.weight", (0, 1))[1],
+                   "head3": 128}.get(k.split(".")[0], 128)
+            if "_linear" in k:
+                fan = store.keys[k.replace("bias", "weight")][1]
+            t = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(fan)
+        else:                                          # BatchNorm beta
+            t = torch.zeros(shp)
+        sd[k] = t
+    for k in store.keys:
+        if k.endswith("running_mean"):
+            sd[k] = torch.zeros(store.keys[k])
+        elif k.endswith("running_var"):
+            sd[k] = torch.ones(store.keys[k])
+        elif k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros((), dtype=torch.int64)
+    store.load_state_dict(sd)
+
+
+class PretrainStep:
+    def __init__(self, K, width=18, stage=1, skeleton="mpii", B=64, R=256, n_data=165894, nce_k=16384, nce_t=0.07,
+                 nce_m=0.5, temperature=0.07, num_samples=400, world_size=1, rank=0, use_graph=True, seed=0,
+                 lr=0.03, momentum=0.9, weight_decay=1e-4):
+        self.K, self.world, self.rank = K, world_size, rank
+        self.lr, self.momentum, self.wd = lr, momentum, weight_decay
+        self.eng = Engine(K, width, stage, skeleton, B, R, n_data, nce_k, nce_t, nce_m, temperature, num_samples,
+                          world_size=world_size)
+        init_parameters(self.eng.store, seed)
+        self.eng.init_banks(seed=seed)               # identical on every rank (all three banks)
+        self.eng.build()
+        self.gen = torch.Generator(device="cuda").manual_seed(1000 + rank)
+        self.use_graph = use_graph
+        if use_graph:
+            self.eng.capture()
+        if world_size > 1:
+            B = self.eng.B
+            self.all_f = torch.empty(world_size * B, 384, device="cuda")
+            self.all_y = torch.empty(world_size * B, dtype=torch.int64, device="cuda")
+
+    @property
+    def launches_per_step(self):
+        return self.eng.launches_per_step
+
+    def draw(self, batch):
+        """Negative indices (memory/alias_multinomial.py:49-65 with uniform probabilities = uniform draw,
+        idx[:,0] = own row, mem_bank.py:176-177) and the dense pixel samples (contrast_trainer.py:674-685)."""
+        e = self.eng
+        idx = torch.randint(0, e.n_data, (e.B, e.K1), device="cuda", generator=self.gen)
+        idx[:, 0] = e.index
+        e.nce_idx.copy_(idx)
+        if e.stage == 2:
+            step = e.R // e.h
+            m = e.depth_mask[:, ::step, ::step][:, :e.h, :e.h].reshape(e.B, -1)
+            has = m.sum(1, keepdim=True) > 0
+            w = torch.where(has, m, torch.ones_like(m))          # rows of dropped samples are ignored downstream
+            e.dense_idx.copy_(torch.multinomial(w, e.S, replacement=True, generator=self.gen))
+
+    def run(self, batch):
+        e = self.eng
+        data = batch
+        e.x.copy_(data[0], non_blocking=True)
+        e.index.copy_(data[1], non_blocking=True)
+        e.skel.copy_(data[2], non_blocking=True)
+        e.joints_yx.copy_(data[4], non_blocking=True)
+        e.joints_vis.copy_(data[5], non_blocking=True)
+        e.use_depth.copy_(data[6], non_blocking=True)
+        e.depth_mask.copy_(data[7], non_blocking=True)
+        self.draw(batch)
+        if self.use_graph:
+            e.graph.replay()
+        else:
+            e.forward()
+            e.backward()
+        if self.world > 1:
+            import torch.distributed as dist
+            h = dist.all_reduce(e.store.g, async_op=True)
+            dist.all_gather_into_tensor(self.all_f, e.f)
+            dist.all_gather_into_tensor(self.all_y, e.index)
+            e.update_banks(self.all_f, self.all_y)
+            h.wait()
+            e.sgd(self.lr, self.momentum, self.wd, 1.0 / self.world)
+        else:
+            e.update_banks()
+            e.sgd(self.lr, self.momentum, self.wd)
+
+    def results(self):
+        return self.eng.results()
+
+    def profile_families(self, batch):
+        """Device time of every C-ABI launch of one real step (CUDA events on the launching stream around
+        each call, no graph), summed per entry point."""
+        e = self.eng
+        saved = [(b, b.clone()) for b in e.store.buffers.values()]
+        g_saved = e.store.g.clone()
+        self.run(batch)                       # make inputs current
+        torch.cuda.synchronize()
+        ev, names = [], []
+
+        def go(prog):
+            for fn, args in prog:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn(*args)
+                b.record()
+                ev.append((a, b))
+                n = getattr(fn, "__name__", "fn")
+                names.append({"fwd_logits": "nce_logits", "bwd": "nce_bwd"}.get(n, n[4:] if n.startswith("hcm_") else n))
+
+        go(e.plan.fwd)
+        e.K.zero(e.store.g, e.store.n * 4)
+        go(e.plan.bwd)
+        torch.cuda.synchronize()
+        fam = {}
+        for (a, b), n in zip(ev, names):
+            d = fam.setdefault(n, {"ms": 0.0, "calls": 0})
+            d["ms"] += a.elapsed_time(b)
+            d["calls"] += 1
+        for b, c in saved:
+            b.copy_(c)
+        e.store.g.copy_(g_saved)
+        return fam

@@ -55,14 +55,17 @@ int hcm_bn_finalize(const float* part, int nparts, int C, long count, const floa
 /* out = act(y*scale + shift + (res*res_scale + res_shift)) */
 int hcm_bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* res_scale,
                  const float* res_shift, int relu, float* out, long P, int C, cudaStream_t stream);
-int hcm_bn_bwd_reduce(const float* dz, const float* mask, const float* y, const float* mean, const float* invstd, long P,
-                      int C, float* part, cudaStream_t stream);
+/* g = dz * [m > 0] with m = mask (if given) else y*mask_scale+mask_shift (if given) else 1 */
+int hcm_bn_bwd_reduce(const float* dz, const float* mask, const float* mask_scale, const float* mask_shift,
+                      const float* y, const float* mean, const float* invstd, long P, int C, float* part,
+                      cudaStream_t stream);
 int hcm_bn_bwd_finalize(const float* part, int nparts, int C, long count, const float* gamma, const float* mean,
                         const float* invstd, float* dgamma, float* dbeta, float* k1, float* k2, float* k3,
                         cudaStream_t stream);
-/* g = dz*[mask>0]; dy = k1*g + k2*y + k3; g_out (+)= g (gradient of the residual branch) */
-int hcm_bn_bwd_apply(const float* dz, const float* mask, const float* y, const float* k1, const float* k2,
-                     const float* k3, float* dy, float* g_out, int g_accumulate, long P, int C, cudaStream_t stream);
+/* dy = k1*g + k2*y + k3 (dy may alias dz); g_out (+)= g (gradient of the residual branch) */
+int hcm_bn_bwd_apply(const float* dz, const float* mask, const float* mask_scale, const float* mask_shift,
+                     const float* y, const float* k1, const float* k2, const float* k3, float* dy, float* g_out,
+                     int g_accumulate, long P, int C, cudaStream_t stream);
 int hcm_relu_bwd(const float* dout, const float* out, float* g, int accumulate, long total, cudaStream_t stream);
 int hcm_axpy(float* dst, const float* src, float alpha, long total, cudaStream_t stream);
 

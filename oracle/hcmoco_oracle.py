@@ -367,7 +367,7 @@ def _top1(logit):
     # learning/util.py:24-38 with target 0: fraction (in %) of rows whose arg-max is column 0
     if logit.shape[0] == 0:
         return torch.tensor(float("nan"))
-    return (logit.argmax(1) == 0).float().mean() * 100.0
+    return (logit.argmax(1) == 0).to(logit.dtype).mean() * 100.0
 
 
 def nce_losses(logits, use_depth=None, use_rgb=None):
@@ -399,7 +399,7 @@ def nce_losses(logits, use_depth=None, use_rgb=None):
 # --------------------------------------------------------------------------------------
 def dense_kept_samples(depth_mask, h):
     """Samples whose nearest-resized mask is non-empty (contrast_trainer.py:674-682)."""
-    m = F.interpolate(depth_mask.unsqueeze(1).float(), size=(h, h), mode="nearest").reshape(depth_mask.shape[0], -1)
+    m = F.interpolate(depth_mask.unsqueeze(1), size=(h, h), mode="nearest").reshape(depth_mask.shape[0], -1)
     return m, m.sum(-1) > 0
 
 
@@ -423,14 +423,14 @@ def dense_loss(G1, G2, depth_mask, sample_idx, use_depth=None, T=0.07):
     d = F.normalize(torch.gather(g2, 2, gi), dim=1)      # [B',C,S]  depth
     L = torch.matmul(d.permute(0, 2, 1), a) / T          # rgb2depth_logits[b,i,j] = <d_i, a_j>/T
     Lt = torch.matmul(a.permute(0, 2, 1), d) / T         # depth2rgb_logits = L^T
-    xy = torch.stack([idx // w, idx % w], -1).float()
+    xy = torch.stack([idx // w, idx % w], -1).to(G1.dtype)
     dist = ((xy.unsqueeze(2) - xy.unsqueeze(1)) ** 2).sum(-1).sqrt()
     soft = torch.softmax(-dist, 1)
     losses = [-(soft * F.log_softmax(L, 1)).sum(-2).mean(),
               -(soft * F.log_softmax(Lt, 1)).sum(-2).mean()]
     tgt = torch.arange(S).unsqueeze(0)
-    accs = [((L.argmax(-2) == tgt).sum(-1).float() / S).mean(),
-            ((Lt.argmax(-2) == tgt).sum(-1).float() / S).mean()]
+    accs = [((L.argmax(-2) == tgt).sum(-1).to(L.dtype) / S).mean(),
+            ((Lt.argmax(-2) == tgt).sum(-1).to(L.dtype) / S).mean()]
     return losses, accs
 
 
@@ -459,7 +459,7 @@ def joint_loss(G1, G2, feat3, joints_yx, joints_vis, use_depth=None, T=0.07):
     accs = []
     for Lx, t in ((Lr, tgt), (Ld, dtgt)):
         cnt = (t != -100).sum(-1)
-        hit = (Lx.argmax(-2) == t).sum(-1).float() / cnt.clamp(min=1)
+        hit = (Lx.argmax(-2) == t).sum(-1).to(Lx.dtype) / cnt.clamp(min=1)
         accs.append(hit[cnt != 0].mean())
     return losses, accs
 
@@ -486,7 +486,7 @@ def scl_loss(G1, G2, joints_yx, use_depth, use_rgb=None, T=0.07):
     off = torch.cat([(use_rgb == 0).view(B, 1).expand(B, J).reshape(-1),
                      (use_depth == 0).view(B, 1).expand(B, J).reshape(-1)])
     pos = pos & ~off.view(-1, 1) & ~off.view(1, -1)
-    pos = pos.float()
+    pos = pos.to(logp.dtype)
     return (-(logp * pos).sum(-1) / pos.sum(-1).clamp(min=1)).mean()
 
 

@@ -1,0 +1,310 @@
+"""Per-kernel numerics: every C-ABI entry point (CUDA, through ctypes) against the plain-PyTorch fp32
+statement of the same op (tests/kernel_ref.py) on the same random inputs.  Tolerance 2e-5 relative
+(fp32 sums in a different order) unless noted."""
+import pytest
+import torch
+
+from kernel_ref import TorchKernels
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def KK():
+    from hcmoco_b200.kernels import CudaKernels
+    return CudaKernels(), TorchKernels(DEV)
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return (scale * torch.randn(*shape, generator=g)).to(DEV)
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp(min=1e-20))
+
+
+def both(KK, name, args, outs, tol=TOL):
+    """Run kernel `name` with the CUDA backend and the reference on cloned arguments; compare args[outs]."""
+    kc, kr = KK
+
+    def cl(a):
+        if not torch.is_tensor(a):
+            return a
+        if a.is_contiguous():
+            return a.clone()
+        c = torch.empty_strided(a.size(), a.stride(), dtype=a.dtype, device=a.device)   # keep row strides (ldx, ldo)
+        c.copy_(a)
+        return c
+
+    a1 = [cl(a) for a in args]
+    a2 = [cl(a) for a in args]
+    getattr(kc, name)(*a1)
+    getattr(kr, name)(*a2)
+    torch.cuda.synchronize()
+    for i in outs:
+        e = rel(a1[i], a2[i])
+        assert e < tol, (name, i, e)
+    return a1, a2
+
+
+CONVS = [  # B, H, W, Cin, Cout, ks, stride
+    (2, 32, 32, 3, 64, 3, 2), (2, 16, 16, 64, 64, 3, 2), (2, 16, 16, 64, 256, 1, 1), (3, 16, 16, 256, 18, 3, 1),
+    (2, 16, 16, 18, 18, 3, 1), (2, 8, 8, 36, 72, 3, 2), (5, 4, 4, 144, 144, 3, 1), (2, 6, 10, 32, 64, 1, 1),
+    (1, 8, 8, 256, 256, 3, 1), (2, 16, 16, 72, 18, 1, 1),
+]
+
+
+def _out_hw(H, W, ks, s):
+    p = (ks - 1) // 2
+    return (H + 2 * p - ks) // s + 1, (W + 2 * p - ks) // s + 1
+
+
+@pytest.mark.parametrize("shape", CONVS)
+@pytest.mark.parametrize("onload", [False, True])
+def test_conv_fwd(KK, shape, onload):
+    B, H, W, Cin, Cout, ks, s = shape
+    Ho, Wo = _out_hw(H, W, ks, s)
+    x, w = rnd(B, H, W, Cin), rnd(Cout, Cin, ks, ks, scale=0.1)
+    sc, sh = (rnd(Cin, seed=1).abs() + 0.5, rnd(Cin, seed=2)) if onload else (None, None)
+    kc, kr = KK
+    rows = kc.conv2d_stat_rows(B, H, W, Cin, Cout, ks, s)
+    y1, y2 = torch.zeros(B, Ho, Wo, Cout, device=DEV), torch.zeros(B, Ho, Wo, Cout, device=DEV)
+    p1, p2 = torch.zeros(rows, 2, Cout, device=DEV), torch.zeros(3, 2, Cout, device=DEV)
+    kc.conv2d_fwd(x, w, None, y1, B, H, W, Cin, Cout, ks, s, sc, sh, 1, p1)
+    kr.conv2d_fwd(x, w, None, y2, B, H, W, Cin, Cout, ks, s, sc, sh, 1, p2)
+    assert rel(y1, y2) < TOL
+    assert rel(p1.sum(0)[1], p2.sum(0)[1]) < TOL
+    assert float((p1.sum(0)[0] - p2.sum(0)[0]).abs().max()) < 1e-4 * float(y2.abs().sum(dim=(0, 1, 2)).max())
+    # bias, no stats
+    bias = rnd(Cout, seed=5)
+    kc.conv2d_fwd(x, w, bias, y1, B, H, W, Cin, Cout, ks, s, None, None, 0, None)
+    kr.conv2d_fwd(x, w, bias, y2, B, H, W, Cin, Cout, ks, s, None, None, 0, None)
+    assert rel(y1, y2) < TOL
+
+
+@pytest.mark.parametrize("shape", CONVS)
+def test_conv_dgrad_wgrad(KK, shape):
+    B, H, W, Cin, Cout, ks, s = shape
+    Ho, Wo = _out_hw(H, W, ks, s)
+    x, w, dy = rnd(B, H, W, Cin), rnd(Cout, Cin, ks, ks, scale=0.1), rnd(B, Ho, Wo, Cout, seed=3)
+    dx = rnd(B, H, W, Cin, seed=4)
+    for acc in (0, 1):
+        both(KK, "conv2d_dgrad", [dy, w, dx, B, H, W, Cin, Cout, ks, s, acc], [2])
+    sc, sh = rnd(Cin, seed=1).abs() + 0.5, rnd(Cin, seed=2)
+    dw = rnd(Cout, Cin, ks, ks, seed=6)
+    both(KK, "conv2d_wgrad", [x, dy, dw, B, H, W, Cin, Cout, ks, s, None, None, 0], [2])
+    both(KK, "conv2d_wgrad", [x, dy, dw, B, H, W, Cin, Cout, ks, s, sc, sh, 1], [2])
+
+
+def test_gemm(KK):
+    A, Bm, C = rnd(4 * 50 * 70), rnd(4 * 70 * 33, seed=1), rnd(4 * 50 * 33, seed=2)
+    bias = rnd(33, seed=3)
+    # plain batched row-major
+    both(KK, "gemm", [A, Bm, None, C, 4, 50, 33, 70, 70, 1, 33, 1, 33, 50 * 70, 70 * 33, 50 * 33, 1.0, 0], [3])
+    # A transposed, B transposed, bias, alpha, accumulate
+    both(KK, "gemm", [A, Bm, bias, C, 4, 50, 33, 70, 1, 50, 1, 70, 33, 50 * 70, 70 * 33, 50 * 33, 0.5, 1], [3])
+    # single tall-K product (the SemGCN / head weight gradients)
+    A2, B2, C2 = rnd(300 * 256), rnd(300 * 128, seed=1), rnd(256 * 128, seed=2)
+    both(KK, "gemm", [A2, B2, None, C2, 1, 256, 128, 300, 1, 256, 128, 1, 128, 0, 0, 0, 1.0, 0], [3])
+
+
+@pytest.mark.parametrize("PC", [(2 * 16 * 16, 18), (3 * 5 * 7, 36), (4096, 64), (39, 128), (2 * 4 * 4, 144), (777, 256)])
+def test_batchnorm(KK, PC):
+    P, C = PC
+    kc, kr = KK
+    y = rnd(P, C) * 2 + 0.3
+    gamma, beta = rnd(C, seed=1).abs() + 0.5, rnd(C, seed=2)
+    outs = []
+    for k in (kc, kr):
+        rows = k.colstat_rows(P, C)
+        part = torch.zeros(rows, 2, C, device=DEV)
+        rm, rv, nbt = torch.zeros(C, device=DEV), torch.ones(C, device=DEV), torch.zeros((), dtype=torch.int64, device=DEV)
+        sc, sh, mu, iv = (torch.zeros(C, device=DEV) for _ in range(4))
+        k.bn_stats(y, P, C, part)
+        k.bn_finalize(part, rows, C, P, gamma, beta, rm, rv, nbt, 0.01, 1e-5, sc, sh, mu, iv)
+        res = rnd(P, C, seed=7)
+        out = torch.zeros(P, C, device=DEV)
+        k.bn_apply(y, sc, sh, res, gamma, beta, 1, out, P, C)
+        # backward with the tensor mask and with the recomputed mask
+        dz = rnd(P, C, seed=8)
+        k1, k2, k3, dg, db = (torch.zeros(C, device=DEV) for _ in range(5))
+        k.bn_bwd_reduce(dz, out, None, None, y, mu, iv, P, C, part)
+        k.bn_bwd_finalize(part, rows, C, P, gamma, mu, iv, dg, db, k1, k2, k3)
+        dy, go = torch.zeros(P, C, device=DEV), rnd(P, C, seed=9)
+        k.bn_bwd_apply(dz, out, None, None, y, k1, k2, k3, dy, go, 1, P, C)
+        k.bn_bwd_reduce(dz, None, sc, sh, y, mu, iv, P, C, part)
+        k1b, k2b, k3b, dgb, dbb = (torch.zeros(C, device=DEV) for _ in range(5))
+        k.bn_bwd_finalize(part, rows, C, P, gamma, mu, iv, dgb, dbb, k1b, k2b, k3b)
+        dz2 = dz.clone()
+        k.bn_bwd_apply(dz2, None, sc, sh, y, k1b, k2b, k3b, dz2, None, 0, P, C)     # in place
+        outs.append((sc, sh, mu, iv, rm, rv, nbt.float(), out, dg, db, dy, go, dgb, dbb, dz2))
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(*outs)):
+        assert rel(a, b) < 5e-5, (i, rel(a, b))
+
+
+def test_elementwise_and_layout(KK):
+    a, b, g = rnd(1000), rnd(1000, seed=1), rnd(1000, seed=2)
+    both(KK, "relu_bwd", [a, b, g, 0, 1000], [2])
+    both(KK, "relu_bwd", [a, b, g, 1, 1000], [2])
+    both(KK, "relu_bwd", [a, b, a, 0, 1000], [2])          # in place
+    both(KK, "axpy", [a, b, 0.25, 1000], [0])
+    x = rnd(3, 6, 8, 8)
+    both(KK, "nchw_to_nhwc", [x, torch.zeros(3, 64, 3, device=DEV), 3, 6, 64, 3, 3], [1])
+    f = rnd(3, 5, 7, 36)
+    both(KK, "avgpool", [f, torch.zeros(3, 100, device=DEV), 3, 35, 36, 100, 18], [1])
+    both(KK, "avgpool_bwd", [rnd(3, 100), rnd(3, 5, 7, 36, seed=1), 1, 3, 35, 36, 100, 18], [1])
+    both(KK, "avgpool_bwd", [rnd(3, 100), rnd(3, 5, 7, 36, seed=1), 0, 3, 35, 36, 100, 18], [1])
+    both(KK, "zero", [rnd(100), 200], [0])
+    both(KK, "colsum_small", [rnd(7, 128), 7, 128, 128, rnd(128, seed=3), 1], [4])
+
+
+@pytest.mark.parametrize("C", [18, 128])
+def test_fuse_and_adjoint(KK, C):
+    B, H, W = 2, 16, 16
+    terms = [rnd(B, H, W, C), rnd(B, H // 2, W // 2, C, seed=1), rnd(B, H // 4, W // 4, C, seed=2),
+             rnd(B, H // 8, W // 8, C, seed=3)]
+    scales = [None, rnd(C, seed=4), rnd(C, seed=5), None]
+    shifts = [None, rnd(C, seed=6), rnd(C, seed=7), None]
+    log2f = torch.tensor([0, 1, 2, 3], dtype=torch.int32)
+    out = torch.zeros(B, H, W, C, device=DEV)
+    both(KK, "fuse_sum", [4, terms, scales, shifts, log2f, None, 1, out, B, H, W, C], [7])
+    both(KK, "fuse_sum", [4, terms, None, None, log2f, rnd(C, seed=8), 0, out, B, H, W, C], [7])
+    both(KK, "fuse_sum", [2, terms[:2], scales[:2], shifts[:2], log2f[:2].clone(), None, 1, out, B, H, W, C], [7])
+    g = rnd(B, H, W, C, seed=9)
+    for k in (1, 2, 3):
+        o = rnd(B, H >> k, W >> k, C, seed=10)
+        both(KK, "upsample_adjoint", [g, o, 0, B, H, W, C, k], [1])
+        both(KK, "upsample_adjoint", [g, o, 1, B, H, W, C, k], [1])
+
+
+def _banks(n):
+    return [torch.nn.functional.normalize(rnd(n, 128, seed=s)) for s in (1, 2, 3)]
+
+
+@pytest.mark.parametrize("BK", [(3, 257), (4, 1025), (2, 16385)])
+def test_nce(KK, BK):
+    B, K1 = BK
+    n = 5000
+    banks = _banks(n)
+    f = torch.nn.functional.normalize(rnd(B, 3, 128), dim=2).reshape(B, 384)
+    idx = torch.randint(0, n, (B, K1), generator=torch.Generator().manual_seed(0)).to(DEV)
+    x = [f[:, 128 * m:128 * (m + 1)] for m in range(3)]
+    kc, kr = KK
+    res = []
+    for use_depth in (None, torch.tensor([1, 0, 1, 1][:B], device=DEV), torch.zeros(B, dtype=torch.int64, device=DEV)):
+        for k in (kc, kr):
+            logits = torch.zeros(6, B, K1, device=DEV)
+            lse, l0, hit, coef = (torch.zeros(6, B, device=DEV) for _ in range(4))
+            loss, acc = torch.zeros(6, device=DEV), torch.zeros(6, device=DEV)
+            df = torch.zeros(B, 384, device=DEV)
+            k.nce_logits(*banks, *x, 384, idx, B, K1, 128, 0.07, logits)
+            k.nce_loss(logits, B, K1, use_depth, None, lse, l0, hit, coef, loss, acc)
+            k.nce_bwd(*banks, *x, 384, idx, B, K1, 128, 0.07, logits, lse, coef, 1.0, df, 384)
+            res.append((logits, lse, loss, acc, coef, df))
+        torch.cuda.synchronize()
+        for i, (a, b) in enumerate(zip(res[-2], res[-1])):
+            assert rel(a, b) < 1e-4 or float((a - b).abs().max()) < 1e-6, (i, rel(a, b))
+
+
+def test_bank_update(KK):
+    n = 1000
+    bank = _banks(n)[0]
+    x = torch.nn.functional.normalize(rnd(6, 3, 128), dim=2).reshape(6, 384)
+    y = torch.tensor([5, 17, 5, 999, 0, 17], device=DEV)          # duplicates: the last writer wins
+    both(KK, "bank_update", [bank, x[:, 128:256], 384, y, 6, 128, 0.5], [0], tol=1e-6)
+
+
+def test_gather_l2norm(KK):
+    B, HW, S = 3, 64, 50
+    src = rnd(B, HW, 128)
+    pix = torch.randint(0, HW, (B, S), generator=torch.Generator().manual_seed(0)).to(DEV)
+    out, inv = torch.zeros(B * S, 128, device=DEV), torch.zeros(B * S, device=DEV)
+    a1, _ = both(KK, "gather_l2norm", [src, 0, pix, HW, S, B * S, 128, out, 128, inv], [7, 9])
+    dsrc = rnd(B, HW, 128, seed=3)
+    both(KK, "gather_l2norm_bwd", [rnd(B * S, 128, seed=2), 128, a1[7], 128, a1[9], pix, HW, S, B * S, 128, dsrc, 0, 1], [10],
+         tol=1e-4)
+    # strided rows, no gather (the projection heads)
+    lin = rnd(B, 128)
+    f, inv2 = torch.zeros(B, 384, device=DEV), torch.zeros(B, device=DEV)
+    a1, _ = both(KK, "gather_l2norm", [lin, 128, None, 0, 1, B, 128, f[:, 128:256], 384, inv2], [7, 9])
+    dlin = torch.zeros(B, 128, device=DEV)
+    both(KK, "gather_l2norm_bwd", [rnd(B, 384, seed=4)[:, 128:256], 384, a1[7], 384, a1[9], None, 0, 1, B, 128, dlin, 128, 0],
+         [10], tol=1e-4)
+
+
+def test_stage2_loss_kernels(KK):
+    kc, kr = KK
+    B, J, h, S, R = 4, 13, 16, 60, 64
+    use_depth = torch.tensor([1, 0, 1, 1], device=DEV)
+    joints = (rnd(B, J, 2) * 40 + 30)
+    both(KK, "joint_pixel_index", [joints, B * J, h, torch.zeros(B, J, dtype=torch.int64, device=DEV)], [3])
+    mask = torch.zeros(B, R, R, device=DEV)
+    mask[0, 10:40, 20:30] = 1
+    mask[2, 1, 1] = 1            # not on the nearest-resize grid -> dropped
+    mask[3, 4, 8] = 1
+    both(KK, "dense_kept", [mask, B, R, h, torch.zeros(B, device=DEV)], [4])
+    kept = torch.tensor([1., 0., 0., 1.], device=DEV)
+    pix = torch.randint(0, h * h, (B, S), generator=torch.Generator().manual_seed(1)).to(DEV)
+    Lm = rnd(B, S, S) * 3
+    stat, fin = torch.zeros(B, 2, S, 4, device=DEV), torch.zeros(8, device=DEV)
+    a1, _ = both(KK, "dense_stats", [Lm, pix, kept, use_depth, B, S, h, stat, fin], [7, 8], tol=1e-4)
+    both(KK, "dense_grad", [Lm, pix, a1[7], kept, a1[8], B, S, h, 1.0], [0], tol=1e-4)
+    # all depth off -> zeros
+    a1, _ = both(KK, "dense_stats", [Lm, pix, kept, torch.zeros_like(use_depth), B, S, h, stat, fin], [8], tol=1e-4)
+    assert float(a1[8][:5].abs().sum()) == 0.0
+    vis = (torch.rand(B, J, generator=torch.Generator().manual_seed(2)) < 0.8).int().to(DEV)
+    Lr, Ld = rnd(B, J, J) * 3, rnd(B, J, J, seed=1) * 3
+    rs, lse, fin = torch.zeros(B, 2, 3, device=DEV), torch.zeros(B, 2, J, device=DEV), torch.zeros(8, device=DEV)
+    a1, _ = both(KK, "joint_stats", [Lr, Ld, vis, use_depth, B, J, rs, lse, fin], [6, 7, 8], tol=1e-4)
+    both(KK, "joint_grad", [Lr, Ld, vis, use_depth, a1[7], a1[8], B, J, 1.0], [0, 1], tol=1e-4)
+    N = 2 * B * J
+    Z = rnd(N, N) * 3
+    rowstat, fin = torch.zeros(N, 3, device=DEV), torch.zeros(4, device=DEV)
+    for ur in (None, torch.tensor([1, 1, 0, 1], device=DEV)):
+        a1, _ = both(KK, "scl_stats", [Z, B, J, ur, use_depth, rowstat, fin], [5, 6], tol=1e-4)
+        both(KK, "scl_grad", [Z, B, J, ur, use_depth, a1[5], a1[6], 1.0], [0], tol=1e-4)
+
+
+@pytest.mark.parametrize("skeleton", ["mpii", "coco_reduce"])
+def test_sgcn_kernels(KK, skeleton):
+    from hcmoco_b200.layout import graph_edges
+    J, rows, cols = graph_edges(skeleton)
+    nnz = len(rows)
+    rows_t = torch.tensor(rows, dtype=torch.int32, device=DEV)
+    cols_t = torch.tensor(cols, dtype=torch.int32, device=DEV)
+    e = rnd(1, nnz) + 1
+    A = torch.zeros(J, J, device=DEV)
+    a1, _ = both(KK, "sgcn_adj", [e, rows_t, cols_t, nnz, J, A], [5])
+    A = a1[5]
+    both(KK, "sgcn_adj_bwd", [A, rnd(J, J, seed=1), rows_t, cols_t, nnz, J, rnd(1, nnz, seed=2), 1], [6])
+    B, Cin = 3, 128
+    x = rnd(B, J, Cin)
+    both(KK, "sgcn_aggregate", [x, A, B, J, Cin, torch.zeros(B, J, 2 * Cin, device=DEV)], [5])
+    dxa = rnd(B, J, 2 * Cin, seed=3)
+    both(KK, "sgcn_aggregate_bwd", [dxa, x, A, B, J, Cin, rnd(B, J, Cin, seed=4), 1, torch.zeros(J, J, device=DEV)], [6, 8],
+         tol=1e-4)
+    both(KK, "sgcn_aggregate_bwd", [dxa, x, A, B, J, Cin, None, 0, torch.zeros(J, J, device=DEV)], [8], tol=1e-4)
+    both(KK, "joint_mean", [x, B, J, Cin, torch.zeros(B, Cin, device=DEV)], [4])
+    both(KK, "joint_mean_bwd", [rnd(B, Cin), B, J, Cin, rnd(B, J, Cin, seed=5), 1], [4])
+
+
+def test_sgd(KK):
+    n = 10007
+    p, g, buf = rnd(n + 1)[:n], rnd(n + 1, seed=1)[:n], rnd(n + 1, seed=2)[:n]
+    both(KK, "sgd_step", [p, g, buf, n, 0.03, 0.9, 1e-4, 1, 1.0], [0, 2], tol=1e-6)
+    both(KK, "sgd_step", [p, g, buf, n, 0.03, 0.9, 1e-4, 0, 0.125], [0, 2], tol=1e-6)
+
+
+def test_missing_library_is_loud(monkeypatch):
+    """No fallback: without the shared library the CUDA backend refuses to construct."""
+    from hcmoco_b200 import _lib
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libhcmoco_sm100.so")
+    monkeypatch.setattr(_lib, "_lib", None)
+    from hcmoco_b200.kernels import CudaKernels
+    with pytest.raises(_lib.HcmError):
+        CudaKernels()
