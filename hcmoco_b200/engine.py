@@ -197,7 +197,7 @@ class Plan:
 
 class Engine:
     def __init__(self, K, width=18, stage=1, skeleton="mpii", B=2, R=224, n_data=20000, nce_k=16384, nce_t=0.07,
-                 nce_m=0.5, temperature=0.07, num_samples=400, feat_dim=128, world_size=1, train=True):
+                 nce_m=0.5, temperature=0.07, num_samples=400, feat_dim=128, world_size=1, train=True, use_tc=True):
         assert feat_dim == 128, "the NCE / loss kernels are specialised for feat_dim=128"
         assert R % 32 == 0, "HRNet needs the input side to be a multiple of 32"
         assert B >= 2, "the reference collapses B=1 (mem_bank.py:39 out.squeeze())"
@@ -208,6 +208,7 @@ class Engine:
         self.n_data, self.K1, self.T_nce, self.m_nce = n_data, nce_k + 1, nce_t, nce_m
         self.T, self.S = temperature, num_samples
         self.world = world_size
+        self.use_tc = use_tc     # tensor-core path for the stride-1 convs (SIMT fp32 implicit GEMM otherwise)
         self.ch = L.WIDTHS[width]
         self.cm = sum(self.ch)
         self.store = ParamStore(K, L.model_keys(width, stage, skeleton, feat_dim))
@@ -281,12 +282,21 @@ class Engine:
         P = B * Ho * Wo
         y = K.empty(B, Ho, Wo, cout)
         w = st.param(ck + ".weight")
-        rows = K.conv2d_stat_rows(B, H, W, cin, cout, ks, stride)
-        assert rows * 2 * cout <= self.part.numel()
+        tc = self.use_tc and bool(K.tc_conv_supported(B, H, W, cin, cout, ks, stride))
         scale, shift, mean, invstd = K.empty(cout), K.empty(cout), K.empty(cout), K.empty(cout)
         bf = st.buffers
         x.consumers += 1
-        p.f(K.conv2d_fwd, x.data, w, None, y, B, H, W, cin, cout, ks, stride, x.scale, x.shift, int(x.relu), self.part)
+        if tc:
+            nb = K.tc_conv_wpack_bytes(B, H, W, cin, cout, ks)
+            wp_f = K.empty((nb + 3) // 4)
+            rows = K.colstat_rows(P, cout)
+            p.f(K.tc_conv_pack, w, wp_f, B, H, W, cin, cout, ks, 0)
+            p.f(K.tc_conv, x.data, wp_f, None, y, B, H, W, cin, cout, ks, x.scale, x.shift, int(x.relu), 0)
+            p.f(K.bn_stats, y, P, cout, self.part)
+        else:
+            rows = K.conv2d_stat_rows(B, H, W, cin, cout, ks, stride)
+            p.f(K.conv2d_fwd, x.data, w, None, y, B, H, W, cin, cout, ks, stride, x.scale, x.shift, int(x.relu), self.part)
+        assert rows * 2 * cout <= self.part.numel()
         p.f(K.bn_finalize, self.part, rows, cout, P, st.param(bk + ".weight"), st.param(bk + ".bias"),
             bf[bk + ".running_mean"], bf[bk + ".running_var"], bf[bk + ".num_batches_tracked"], BN2D_MOMENTUM, BN_EPS,
             scale, shift, mean, invstd)
@@ -313,9 +323,16 @@ class Engine:
                 if x.lazy:
                     assert x.consumers == 1 and x.grad is None
                     x.grad = K.empty(B, H, W, cin)
-                    p.b(K.conv2d_dgrad, dy, w, x.grad, B, H, W, cin, cout, ks, stride, 0)
+                    gx, acc = x.grad, 0
                 else:
                     gx, acc = p.grad(x)
+                if tc and K.tc_conv_supported(B, H, W, cout, cin, ks, stride):
+                    # data gradient = the same tensor-core conv run on dy with transposed + flipped weights
+                    nbt = K.tc_conv_wpack_bytes(B, H, W, cout, cin, ks)
+                    wp_t = K.empty((nbt + 3) // 4)
+                    p.b(K.tc_conv_pack, w, wp_t, B, H, W, cout, cin, ks, 1)
+                    p.b(K.tc_conv, dy, wp_t, None, gx, B, H, W, cout, cin, ks, None, None, 0, acc)
+                else:
                     p.b(K.conv2d_dgrad, dy, w, gx, B, H, W, cin, cout, ks, stride, acc)
 
         p.on_backward(backward)
@@ -611,7 +628,12 @@ class Engine:
             o += n
             ft.consumers += 1
             y = K.empty(B, ft.H, ft.W, 128)
-            p.f(K.conv2d_fwd, ft.data, ws[j], None, y, B, ft.H, ft.W, ft.C, 128, 1, 1, None, None, 0, None)
+            if self.use_tc and K.tc_conv_supported(B, ft.H, ft.W, ft.C, 128, 1, 1):
+                wp = K.empty((K.tc_conv_wpack_bytes(B, ft.H, ft.W, ft.C, 128, 1) + 3) // 4)
+                p.f(K.tc_conv_pack, ws[j], wp, B, ft.H, ft.W, ft.C, 128, 1, 0)
+                p.f(K.tc_conv, ft.data, wp, None, y, B, ft.H, ft.W, ft.C, 128, 1, None, None, 0, 0)
+            else:
+                p.f(K.conv2d_fwd, ft.data, ws[j], None, y, B, ft.H, ft.W, ft.C, 128, 1, 1, None, None, 0, None)
             ys.append(y)
         out = Act(K.empty(B, h, h, 128), B, h, h, 128)
         log2f = torch.tensor([0, 1, 2, 3], dtype=torch.int32)
@@ -632,7 +654,12 @@ class Engine:
                     p.b(K.upsample_adjoint, G, Gj, 0, B, h, h, 128, j)
                 p.b(K.conv2d_wgrad, ft.data, Gj, gs[j], B, ft.H, ft.W, ft.C, 128, 1, 1, None, None, 0)
                 gx, acc = p.grad(ft)
-                p.b(K.conv2d_dgrad, Gj, ws[j], gx, B, ft.H, ft.W, ft.C, 128, 1, 1, acc)
+                if self.use_tc and K.tc_conv_supported(B, ft.H, ft.W, 128, ft.C, 1, 1):
+                    wpt = K.empty((K.tc_conv_wpack_bytes(B, ft.H, ft.W, 128, ft.C, 1) + 3) // 4)
+                    p.b(K.tc_conv_pack, ws[j], wpt, B, ft.H, ft.W, 128, ft.C, 1, 1)
+                    p.b(K.tc_conv, Gj, wpt, None, gx, B, ft.H, ft.W, 128, ft.C, 1, None, None, 0, acc)
+                else:
+                    p.b(K.conv2d_dgrad, Gj, ws[j], gx, B, ft.H, ft.W, ft.C, 128, 1, 1, acc)
 
         p.on_backward(backward)
         return out

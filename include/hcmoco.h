@@ -45,6 +45,19 @@ int hcm_gemm(const float* A, const float* Bm, const float* bias, float* C, int b
              long sAk, long sBk, long sBn, long sCm, long bsA, long bsB, long bsC, float alpha, int accumulate,
              cudaStream_t stream);
 
+/* ---- tensor-core convolution (tc_conv.cu): tcgen05.mma (bf16 hi/lo split, fp32 accumulate in TMEM), weights
+ *      streamed by cp.async.bulk (TMA) — the stride-1 3x3 / 1x1 nn.Conv2d layers of official_hrnet.py:26-29,
+ *      68-75, 187-216 and the 1x1 projection build_backbone.py:243-245; forward and data gradient ---- */
+int hcm_tc_conv_supported(int B, int H, int W, int Cin, int Cout, int ks, int stride);
+long hcm_tc_conv_wpack_bytes(int B, int H, int W, int Cin, int Cout, int ks);
+/* transpose=0: pack w[Cout][Cin][ks][ks] for the forward conv; transpose=1: pack the same tensor for its data
+ * gradient seen as a conv with Cin' = Cout(w), Cout' = Cin(w) (pass those as Cin, Cout) */
+int hcm_tc_conv_pack(const float* w, void* wpack, int B, int H, int W, int Cin, int Cout, int ks, int transpose,
+                     cudaStream_t stream);
+/* y[B,H,W,Cout] (+)= conv(T(x[B,H,W,Cin])) (+bias), stride 1, pad (ks-1)/2 */
+int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, int B, int H, int W, int Cin, int Cout,
+                int ks, const float* in_scale, const float* in_shift, int in_relu, int accumulate, cudaStream_t stream);
+
 /* ---- train-mode batch norm (bn.cu) : nn.BatchNorm2d(momentum=0.01) official_hrnet.py:22-23 (+ReLU /
  *      residual add :44-60, :86-101) and nn.BatchNorm1d networks/SGCN/sem_gcn.py:13 ---- */
 int hcm_colstat_rows(long P, int C);

@@ -100,6 +100,33 @@ class TorchKernels:
         dw.reshape(-1).add_(g.reshape(-1))
         return 0
 
+    # ---------------------------------------------------------------- tc_conv.cu (exact fp32 statement)
+    def tc_conv_supported(self, B, H, W, Cin, Cout, ks, stride):
+        return int(stride == 1 and ks in (1, 3) and Cin % 2 == 0 and Cout % 2 == 0 and Cin <= 256 and Cout <= 256)
+
+    def tc_conv_wpack_bytes(self, B, H, W, Cin, Cout, ks):
+        return Cin * Cout * ks * ks * 8          # room for fp64 in the exact-wiring tests
+
+    def tc_conv_pack(self, w, wpack, B, H, W, Cin, Cout, ks, transpose):
+        # the "packed" form of the reference is simply the effective OIHW weight of the GEMM being run
+        wv = w.reshape(-1)[:Cin * Cout * ks * ks]
+        if transpose:
+            weff = wv.reshape(Cin, Cout, ks, ks).transpose(0, 1).flip(2, 3)     # w is [Cout(w)=Cin'][Cin(w)=Cout']
+        else:
+            weff = wv.reshape(Cout, Cin, ks, ks)
+        wpack.reshape(-1).view(w.dtype)[:weff.numel()].copy_(weff.reshape(-1))
+        return 0
+
+    def tc_conv(self, x, wpack, bias, y, B, H, W, Cin, Cout, ks, sc, sh, relu, accumulate):
+        weff = wpack.reshape(-1).view(x.dtype)[:Cin * Cout * ks * ks].reshape(Cout, Cin, ks, ks)
+        xin = _tf(x, sc, sh, relu, Cin).reshape(B, H, W, Cin).permute(0, 3, 1, 2)
+        o = _nhwc(F.conv2d(xin, weff, bias, 1, (ks - 1) // 2)).reshape(-1)
+        if accumulate:
+            y.reshape(-1).add_(o)
+        else:
+            y.reshape(-1).copy_(o)
+        return 0
+
     def gemm(self, A, Bm, bias, C, batch, M, N, K, sAm, sAk, sBk, sBn, sCm, bsA, bsB, bsC, alpha, accumulate):
         a = torch.as_strided(A.reshape(-1), (batch, M, K), (bsA, sAm, sAk))
         b = torch.as_strided(Bm.reshape(-1), (batch, K, N), (bsB, sBk, sBn))

@@ -14,6 +14,9 @@ TOL = 2e-5
 @pytest.fixture(scope="module")
 def KK():
     from hcmoco_b200.kernels import CudaKernels
+    # the PyTorch reference must be true fp32: cuDNN / cuBLAS default to TF32 on this GPU
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     return CudaKernels(), TorchKernels(DEV)
 
 
@@ -308,3 +311,43 @@ def test_missing_library_is_loud(monkeypatch):
     from hcmoco_b200.kernels import CudaKernels
     with pytest.raises(_lib.HcmError):
         CudaKernels()
+
+
+TC_CONVS = [  # B, H, W, Cin, Cout, ks
+    (2, 16, 16, 18, 18, 3), (2, 16, 16, 64, 64, 3), (3, 8, 8, 144, 144, 3), (2, 16, 16, 64, 256, 1), (2, 16, 16, 256, 64, 1),
+    (2, 16, 16, 256, 18, 3), (2, 32, 32, 36, 36, 3), (4, 64, 64, 18, 18, 3), (2, 8, 8, 72, 18, 1), (1, 12, 12, 256, 256, 3),
+    (2, 16, 16, 32, 128, 1), (3, 4, 4, 128, 128, 3), (2, 96, 96, 32, 32, 3),
+]
+
+
+@pytest.mark.parametrize("shape", TC_CONVS)
+def test_tc_conv(KK, shape):
+    """tcgen05 bf16-split convolution against exact fp32 (F.conv2d, TF32 off).  Bar 3e-5 relative: the dropped
+    lo*lo term and the bf16 rounding of lo are ~2^-17 per product."""
+    B, H, W, Cin, Cout, ks = shape
+    kc, kr = KK
+    assert kc.tc_conv_supported(B, H, W, Cin, Cout, ks, 1)
+    x, w = rnd(B, H, W, Cin), rnd(Cout, Cin, ks, ks, scale=0.1)
+    sc, sh = rnd(Cin, seed=1).abs() + 0.5, rnd(Cin, seed=2)
+    bias = rnd(Cout, seed=5)
+    wp = torch.zeros((kc.tc_conv_wpack_bytes(B, H, W, Cin, Cout, ks) + 3) // 4, device=DEV)
+    kc.tc_conv_pack(w, wp, B, H, W, Cin, Cout, ks, 0)
+    y1, y2 = rnd(B, H, W, Cout, seed=7), rnd(B, H, W, Cout, seed=7)
+    # forward, BN+ReLU applied on load
+    kc.tc_conv(x, wp, None, y1, B, H, W, Cin, Cout, ks, sc, sh, 1, 0)
+    kr.conv2d_fwd(x, w, None, y2, B, H, W, Cin, Cout, ks, 1, sc, sh, 1, None)
+    assert rel(y1, y2) < 3e-5, rel(y1, y2)
+    # plain + bias + accumulate
+    kc.tc_conv(x, wp, bias, y1, B, H, W, Cin, Cout, ks, None, None, 0, 1)
+    y3 = torch.zeros_like(y2)
+    kr.conv2d_fwd(x, w, bias, y3, B, H, W, Cin, Cout, ks, 1, None, None, 0, None)
+    assert rel(y1, y2 + y3) < 3e-5
+    # data gradient through the transposed pack
+    if kc.tc_conv_supported(B, H, W, Cout, Cin, ks, 1):
+        dy = rnd(B, H, W, Cout, seed=9)
+        wpt = torch.zeros((kc.tc_conv_wpack_bytes(B, H, W, Cout, Cin, ks) + 3) // 4, device=DEV)
+        kc.tc_conv_pack(w, wpt, B, H, W, Cout, Cin, ks, 1)
+        dx1, dx2 = torch.zeros(B, H, W, Cin, device=DEV), torch.zeros(B, H, W, Cin, device=DEV)
+        kc.tc_conv(dy, wpt, None, dx1, B, H, W, Cout, Cin, ks, None, None, 0, 0)
+        kr.conv2d_dgrad(dy, w, dx2, B, H, W, Cin, Cout, ks, 1, 0)
+        assert rel(dx1, dx2) < 3e-5, rel(dx1, dx2)
