@@ -23,7 +23,7 @@ def parse_header(path=HEADER):
     src = open(path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     protos = []
-    for m in re.finditer(r"(?:^|\n)\s*(int|const char\*)\s+(hcm_\w+)\s*\(([^)]*)\)\s*;", src):
+    for m in re.finditer(r"(?:^|\n)\s*(int|long|const char\*)\s+(hcm_\w+)\s*\(([^)]*)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         argl = []
         if args and args != "void":
@@ -38,7 +38,7 @@ def parse_header(path=HEADER):
                 else:
                     ct = _SCALARS[typ]
                 argl.append((ct, an))
-        protos.append((name, ctypes.c_char_p if "char" in ret else ctypes.c_int, argl))
+        protos.append((name, ctypes.c_char_p if "char" in ret else (ctypes.c_long if ret == "long" else ctypes.c_int), argl))
     return protos
 
 
