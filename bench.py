@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--detail", default=None, help="write the per-shape conv timing table to this file")
     return ap.parse_args()
 
 
@@ -228,6 +229,10 @@ def run_engine(a):
     d2h = 32 * 4
     # per-kernel-family device time inside one real step (events around every C-ABI launch, no graph)
     fam = step.profile_families(dev[0])
+    if a.detail and rank == 0:
+        with open(a.detail, "w") as f:
+            for k, v in sorted(step.detail.items(), key=lambda kv: -kv[1]["ms"]):
+                f.write("%9.3f ms %4d calls %8.1f us/call  %s\n" % (v["ms"], v["calls"], 1e3 * v["ms"] / v["calls"], k))
     step_ms = ms_dev / a.steps
     value = a.batch * world * a.steps / (ms_dev / 1e3)
     e2e = a.batch * world * a.steps / (ms_e2e / 1e3)

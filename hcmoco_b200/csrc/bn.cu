@@ -100,22 +100,30 @@ __global__ void colstat_kernel(const float* __restrict__ a, const float* __restr
   }
 }
 
-// one warp per channel: fp64 reduction of the partial rows, then the per-channel coefficients
-__global__ void bn_finalize_kernel(const float* __restrict__ part, int nparts, int C, double count,
+// one CTA (128 threads) per channel: fp64 reduction of the partial rows, then the per-channel coefficients
+__device__ __forceinline__ void block_sum2_d(double& s, double& q, double* red) {
+  s = warp_sum_d(s); q = warp_sum_d(q);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[w] = s; red[4 + w] = q; }
+  __syncthreads();
+  s = red[0] + red[1] + red[2] + red[3];
+  q = red[4] + red[5] + red[6] + red[7];
+}
+
+__global__ void __launch_bounds__(128) bn_finalize_kernel(const float* __restrict__ part, int nparts, int C, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
                                    float* scale, float* shift, float* mean_out, float* invstd_out) {
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+  __shared__ double red[8];
+  const int c = blockIdx.x;
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
-  if (c >= C) return;
   double s = 0.0, q = 0.0;
-  for (int i = lane; i < nparts; i += 32) {
+  for (int i = threadIdx.x; i < nparts; i += 128) {
     s += (double)part[((long)i * 2 + 0) * C + c];
     q += (double)part[((long)i * 2 + 1) * C + c];
   }
-  s = warp_sum_d(s); q = warp_sum_d(q);
-  if (lane == 0) {
+  block_sum2_d(s, q, red);
+  if (threadIdx.x == 0) {
     const double m = s / count;
     double var = q / count - m * m;
     if (var < 0.0) var = 0.0;
@@ -134,20 +142,19 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int nparts, i
 }
 
 // backward finalize: dgamma, dbeta and dy = k1*g + k2*y + k3
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, double count,
+__global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, double count,
                                        const float* __restrict__ gamma, const float* __restrict__ mean,
                                        const float* __restrict__ invstd, float* dgamma, float* dbeta, float* k1, float* k2,
                                        float* k3) {
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (c >= C) return;
+  __shared__ double red[8];
+  const int c = blockIdx.x;
   double s = 0.0, q = 0.0;
-  for (int i = lane; i < nparts; i += 32) {
+  for (int i = threadIdx.x; i < nparts; i += 128) {
     s += (double)part[((long)i * 2 + 0) * C + c];
     q += (double)part[((long)i * 2 + 1) * C + c];
   }
-  s = warp_sum_d(s); q = warp_sum_d(q);
-  if (lane == 0) {
+  block_sum2_d(s, q, red);
+  if (threadIdx.x == 0) {
     const float g = gamma ? gamma[c] : 1.f;
     const double is = invstd[c], mu = mean[c];
     if (dgamma) dgamma[c] = (float)q;
@@ -302,7 +309,7 @@ int hcm_bn_finalize(const float* part, int nparts, int C, long count, const floa
                     float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                     float* scale, float* shift, float* mean, float* invstd, cudaStream_t stream) {
   HCM_CHECK_ARG(part && scale && shift && mean && invstd && nparts >= 1, "bn_finalize: bad args");
-  bn_finalize_kernel<<<hcm_cdiv(C, 4), 128, 0, stream>>>(part, nparts, C, (double)count, gamma, beta, running_mean,
+  bn_finalize_kernel<<<C, 128, 0, stream>>>(part, nparts, C, (double)count, gamma, beta, running_mean,
                                                          running_var, num_batches_tracked, momentum, eps, scale, shift,
                                                          mean, invstd);
   HCM_LAUNCH_CHECK("bn_finalize");
@@ -342,7 +349,7 @@ int hcm_bn_bwd_finalize(const float* part, int nparts, int C, long count, const 
                         const float* invstd, float* dgamma, float* dbeta, float* k1, float* k2, float* k3,
                         cudaStream_t stream) {
   HCM_CHECK_ARG(part && mean && invstd && k1 && k2 && k3, "bn_bwd_finalize: bad args");
-  bn_bwd_finalize_kernel<<<hcm_cdiv(C, 4), 128, 0, stream>>>(part, nparts, C, (double)count, gamma, mean, invstd, dgamma,
+  bn_bwd_finalize_kernel<<<C, 128, 0, stream>>>(part, nparts, C, (double)count, gamma, mean, invstd, dgamma,
                                                              dbeta, k1, k2, k3);
   HCM_LAUNCH_CHECK("bn_bwd_finalize");
   return HCM_OK;

@@ -317,8 +317,11 @@ class Engine:
             p.b(K.bn_bwd_apply, spec["dz"], spec["mask"], msc, msh, y, self.k1, self.k2, self.k3, spec["dy"],
                 spec["g_out"], spec["g_acc"], P, cout)
             dy = spec["dy"]
-            p.b(K.conv2d_wgrad, x.data, dy, st.grad(ck + ".weight"), B, H, W, cin, cout, ks, stride, x.scale, x.shift,
-                int(x.relu))
+            if self.use_tc and K.tc_wgrad_supported(B, H, W, cin, cout, ks, stride):
+                p.b(K.tc_wgrad, x.data, dy, st.grad(ck + ".weight"), B, H, W, cin, cout, ks, x.scale, x.shift, int(x.relu))
+            else:
+                p.b(K.conv2d_wgrad, x.data, dy, st.grad(ck + ".weight"), B, H, W, cin, cout, ks, stride, x.scale, x.shift,
+                    int(x.relu))
             if x.needs_grad:
                 if x.lazy:
                     assert x.consumers == 1 and x.grad is None
@@ -652,7 +655,10 @@ class Engine:
                 else:
                     Gj = K.empty(B, ft.H, ft.W, 128)
                     p.b(K.upsample_adjoint, G, Gj, 0, B, h, h, 128, j)
-                p.b(K.conv2d_wgrad, ft.data, Gj, gs[j], B, ft.H, ft.W, ft.C, 128, 1, 1, None, None, 0)
+                if self.use_tc and K.tc_wgrad_supported(B, ft.H, ft.W, ft.C, 128, 1, 1):
+                    p.b(K.tc_wgrad, ft.data, Gj, gs[j], B, ft.H, ft.W, ft.C, 128, 1, None, None, 0)
+                else:
+                    p.b(K.conv2d_wgrad, ft.data, Gj, gs[j], B, ft.H, ft.W, ft.C, 128, 1, 1, None, None, 0)
                 gx, acc = p.grad(ft)
                 if self.use_tc and K.tc_conv_supported(B, ft.H, ft.W, 128, ft.C, 1, 1):
                     wpt = K.empty((K.tc_conv_wpack_bytes(B, ft.H, ft.W, 128, ft.C, 1) + 3) // 4)

@@ -132,7 +132,7 @@ class PretrainStep:
         g_saved = e.store.g.clone()
         self.run(batch)                       # make inputs current
         torch.cuda.synchronize()
-        ev, names = [], []
+        ev, names, shapes = [], [], []
 
         def go(prog):
             for fn, args in prog:
@@ -142,17 +142,28 @@ class PretrainStep:
                 b.record()
                 ev.append((a, b))
                 n = getattr(fn, "__name__", "fn")
-                names.append({"fwd_logits": "nce_logits", "bwd": "nce_bwd"}.get(n, n[4:] if n.startswith("hcm_") else n))
+                n = {"fwd_logits": "nce_logits", "bwd": "nce_bwd"}.get(n, n[4:] if n.startswith("hcm_") else n)
+                names.append(n)
+                o = {"tc_conv": 4, "conv2d_fwd": 4, "conv2d_dgrad": 3, "conv2d_wgrad": 3, "tc_wgrad": 3}.get(n)
+                shapes.append(None if o is None else "%s %dx%d %d->%d k%d%s" % (
+                    n, args[o + 1], args[o + 2], args[o + 3], args[o + 4], args[o + 5],
+                    "" if n.startswith("tc_") else " s%d" % args[o + 6]))
 
         go(e.plan.fwd)
         e.K.zero(e.store.g, e.store.n * 4)
         go(e.plan.bwd)
         torch.cuda.synchronize()
         fam = {}
-        for (a, b), n in zip(ev, names):
+        self.detail = {}
+        for (a, b), n, sh in zip(ev, names, shapes):
             d = fam.setdefault(n, {"ms": 0.0, "calls": 0})
-            d["ms"] += a.elapsed_time(b)
+            t = a.elapsed_time(b)
+            d["ms"] += t
             d["calls"] += 1
+            if sh is not None:
+                dd = self.detail.setdefault(sh, {"ms": 0.0, "calls": 0})
+                dd["ms"] += t
+                dd["calls"] += 1
         for b, c in saved:
             b.copy_(c)
         e.store.g.copy_(g_saved)

@@ -58,6 +58,11 @@ int hcm_tc_conv_pack(const float* w, void* wpack, int B, int H, int W, int Cin, 
 int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, int B, int H, int W, int Cin, int Cout,
                 int ks, const float* in_scale, const float* in_shift, int in_relu, int accumulate, cudaStream_t stream);
 
+/* tensor-core weight gradient (tc_wgrad.cu): dw[Cout,Cin,ks,ks] += sum_pixels dy * T(x), stride 1 */
+int hcm_tc_wgrad_supported(int B, int H, int W, int Cin, int Cout, int ks, int stride);
+int hcm_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int Cout, int ks,
+                 const float* in_scale, const float* in_shift, int in_relu, cudaStream_t stream);
+
 /* ---- train-mode batch norm (bn.cu) : nn.BatchNorm2d(momentum=0.01) official_hrnet.py:22-23 (+ReLU /
  *      residual add :44-60, :86-101) and nn.BatchNorm1d networks/SGCN/sem_gcn.py:13 ---- */
 int hcm_colstat_rows(long P, int C);

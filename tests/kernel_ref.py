@@ -127,6 +127,12 @@ class TorchKernels:
             y.reshape(-1).copy_(o)
         return 0
 
+    def tc_wgrad_supported(self, B, H, W, Cin, Cout, ks, stride):
+        return self.tc_conv_supported(B, H, W, Cin, Cout, ks, stride)
+
+    def tc_wgrad(self, x, dy, dw, B, H, W, Cin, Cout, ks, sc, sh, relu):
+        return self.conv2d_wgrad(x, dy, dw, B, H, W, Cin, Cout, ks, 1, sc, sh, relu)
+
     def gemm(self, A, Bm, bias, C, batch, M, N, K, sAm, sAk, sBk, sBn, sCm, bsA, bsB, bsC, alpha, accumulate):
         a = torch.as_strided(A.reshape(-1), (batch, M, K), (bsA, sAm, sAk))
         b = torch.as_strided(Bm.reshape(-1), (batch, K, N), (bsB, sBk, sBn))

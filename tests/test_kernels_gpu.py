@@ -351,3 +351,21 @@ def test_tc_conv(KK, shape):
         kc.tc_conv(dy, wpt, None, dx1, B, H, W, Cout, Cin, ks, None, None, 0, 0)
         kr.conv2d_dgrad(dy, w, dx2, B, H, W, Cin, Cout, ks, 1, 0)
         assert rel(dx1, dx2) < 3e-5, rel(dx1, dx2)
+
+
+@pytest.mark.parametrize("shape", TC_CONVS)
+def test_tc_wgrad(KK, shape):
+    """tcgen05 weight gradient (both operands MN-major, accumulators resident in TMEM across tiles)."""
+    B, H, W, Cin, Cout, ks = shape
+    kc, kr = KK
+    assert kc.tc_wgrad_supported(B, H, W, Cin, Cout, ks, 1)
+    x, dy = rnd(B, H, W, Cin), rnd(B, H, W, Cout, seed=3)
+    sc, sh = rnd(Cin, seed=1).abs() + 0.5, rnd(Cin, seed=2)
+    dw1 = rnd(Cout, Cin, ks, ks, seed=6)
+    dw2 = dw1.clone()
+    kc.tc_wgrad(x, dy, dw1, B, H, W, Cin, Cout, ks, sc, sh, 1)
+    kr.conv2d_wgrad(x, dy, dw2, B, H, W, Cin, Cout, ks, 1, sc, sh, 1)
+    assert rel(dw1, dw2) < 3e-5, rel(dw1, dw2)
+    kc.tc_wgrad(x, dy, dw1, B, H, W, Cin, Cout, ks, None, None, 0)
+    kr.conv2d_wgrad(x, dy, dw2, B, H, W, Cin, Cout, ks, 1, None, None, 0)
+    assert rel(dw1, dw2) < 3e-5, rel(dw1, dw2)
