@@ -25,15 +25,17 @@
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int NTHREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: transform + epilogue
-constexpr int WSTAGES = 4;
+constexpr int NTRANS = 256;                  // transform threads: warps 2..9
+constexpr int NTHREADS = 64 + NTRANS + 128;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 10..13: epilogue
 constexpr int MAXG = 8;
-constexpr int HDR_BYTES = 4096;   // barriers, tmem pointer, scale/shift (2 x 256 floats)
+constexpr int HDR_BYTES = 8192;              // barriers, tmem pointer, scale/shift (2 x 256 floats), position tables (2 x 512 int)
+constexpr int MAX_LPAD = 512;
 
 struct Geo {
   int Hp, Wp, L, Lpad, Npad, Cin16, ngroups, cg[MAXG], cgmax, nsteps, tmem_cols;
-  long Mv;
-  size_t smem;
+  int nastage, acc_stages, w_resident, wst, grid;
+  long Mv, tiles;
+  size_t a_stage_bytes, wbytes, smem;
 };
 
 Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks) {
@@ -41,11 +43,14 @@ Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks) {
   g.Hp = (ks == 3) ? H + 2 : H;
   g.Wp = (ks == 3) ? W + 2 : W;
   g.Mv = (long)B * g.Hp * g.Wp;
+  g.tiles = (g.Mv + TILE_M - 1) / TILE_M;
   g.L = (ks == 3) ? TILE_M + 2 * (g.Wp + 1) : TILE_M;
   g.Lpad = ceil_to(g.L, 8);
   g.Npad = ceil_to(Cout, 16);
   g.Cin16 = ceil_to(Cin, 16);
-  int max_cg = (int)((96 * 1024) / (4 * g.Lpad)) / 16 * 16;
+  const size_t wslab = (size_t)64 * g.Npad;
+  // channel groups: one staged A buffer holds <= cgmax channels of the halo (hi + lo planes)
+  int max_cg = (int)((72 * 1024) / (4 * g.Lpad)) / 16 * 16;
   if (max_cg > 128) max_cg = 128;
   if (max_cg < 16) max_cg = 16;
   g.ngroups = (g.Cin16 + max_cg - 1) / max_cg;
@@ -53,22 +58,31 @@ Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks) {
   int left = g.Cin16;
   g.cgmax = 0;
   g.nsteps = 0;
-  for (int i = 0; i < g.ngroups; ++i) {
+  for (int i = 0; i < g.ngroups && i < MAXG; ++i) {
     g.cg[i] = left < per ? left : per;
     left -= g.cg[i];
     if (g.cg[i] > g.cgmax) g.cgmax = g.cg[i];
     g.nsteps += ks * ks * (g.cg[i] / 16);
   }
+  g.a_stage_bytes = (size_t)4 * g.cgmax * g.Lpad;
+  g.acc_stages = (2 * g.Npad <= 512) ? 2 : 1;
   int c = 32;
-  while (c < g.Npad) c <<= 1;
+  while (c < g.acc_stages * g.Npad) c <<= 1;
   g.tmem_cols = c;
-  g.smem = HDR_BYTES + (size_t)4 * g.cgmax * g.Lpad + (size_t)WSTAGES * 64 * g.Npad;
+  g.wbytes = (size_t)g.nsteps * wslab;
+  const size_t budget = 220 * 1024 - HDR_BYTES;
+  g.nastage = (2 * g.a_stage_bytes + (g.wbytes < 8 * wslab ? g.wbytes : 8 * wslab) <= budget) ? 2 : 1;
+  const size_t left_b = budget - g.nastage * g.a_stage_bytes;
+  g.w_resident = g.wbytes <= left_b ? 1 : 0;
+  g.wst = g.w_resident ? 0 : (int)(left_b / wslab > 8 ? 8 : left_b / wslab);
+  g.smem = HDR_BYTES + g.nastage * g.a_stage_bytes + (g.w_resident ? g.wbytes : (size_t)g.wst * wslab);
+  g.grid = (int)(g.tiles < 148 ? g.tiles : 148);
   return g;
 }
 
 bool geo_ok(const Geo& g, int Cin, int Cout, int ks) {
   return (ks == 1 || ks == 3) && Cin <= 256 && Cout <= 256 && (Cout % 2) == 0 && (Cin % 2) == 0 && g.ngroups <= MAXG &&
-         g.smem <= 220 * 1024 && g.Lpad * 16 < (1 << 18);
+         g.Lpad <= MAX_LPAD && g.Mv < (1L << 31) && (g.w_resident || g.wst >= 2) && g.smem <= 225 * 1024;
 }
 
 struct TcParams {
@@ -84,19 +98,34 @@ struct TcParams {
   Geo g;
 };
 
+// virtual position -> pixel index of the unpadded [B,H,W] tensor, or -1 for padding / out of range
+__device__ __forceinline__ int virt_to_pixel(long pv, const TcParams& p) {
+  const Geo& g = p.g;
+  if (pv < 0 || pv >= g.Mv) return -1;
+  if (p.ks != 3) return (int)pv;
+  const unsigned v = (unsigned)pv, hw = (unsigned)(g.Hp * g.Wp);
+  const unsigned b = v / hw, rem = v - b * hw;
+  const unsigned row = rem / (unsigned)g.Wp, col = rem - row * (unsigned)g.Wp;
+  if (row < 1 || row > (unsigned)p.H || col < 1 || col > (unsigned)p.W) return -1;
+  return (int)((b * p.H + row - 1) * p.W + (col - 1));
+}
+
 // ------------------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(NTHREADS) tc_conv_kernel(const TcParams p) {
+// Persistent: CTA b owns tiles b, b+grid, ...  Pipelines: staged A buffers (transform <-> MMA), TMEM accumulator
+// stages (MMA <-> epilogue), weights resident in shared memory (one bulk copy) or streamed through a ring.
+__global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Geo& g = p.g;
-  // header
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);            // [0..3] wfull, [4..7] wempty, 8 a_ready, 9 a_free, 10 acc_ready
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + 128);
+  // barriers: 0,1 a_full  2,3 a_empty  4,5 acc_full  6,7 acc_empty  8 w_full(resident)  16.. ring full, 24.. ring empty
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + 512);
   float* s_sc = reinterpret_cast<float*>(smem + 1024);
   float* s_sh = s_sc + 256;
-  uint8_t* A_hi = smem + HDR_BYTES;
-  const uint32_t plane = (uint32_t)g.Lpad * 16;                  // bytes per 8-channel plane
-  uint8_t* A_lo = A_hi + (size_t)(g.cgmax / 8) * plane;
-  uint8_t* Wring = A_hi + (size_t)4 * g.cgmax * g.Lpad;
+  int* s_src = reinterpret_cast<int*>(smem + 3072);               // [2][MAX_LPAD]
+  uint8_t* Abase = smem + HDR_BYTES;
+  const uint32_t plane = (uint32_t)g.Lpad * 16;
+  const uint32_t lo_off = (uint32_t)(g.cgmax / 8) * plane;        // A_lo planes follow the A_hi planes of a stage
+  uint8_t* Wbase = Abase + (size_t)g.nastage * g.a_stage_bytes;
   const uint32_t wslab = 64u * g.Npad;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,15 +133,17 @@ __global__ void __launch_bounds__(NTHREADS) tc_conv_kernel(const TcParams p) {
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < WSTAGES; ++s) { mbar_init(BAR(s), 1); mbar_init(BAR(4 + s), 1); }
-    mbar_init(BAR(8), 128);
-    mbar_init(BAR(9), 1);
-    mbar_init(BAR(10), 1);
+    mbar_init(BAR(0), NTRANS); mbar_init(BAR(1), NTRANS);
+    mbar_init(BAR(2), 1); mbar_init(BAR(3), 1);
+    mbar_init(BAR(4), 1); mbar_init(BAR(5), 1);
+    mbar_init(BAR(6), 128); mbar_init(BAR(7), 128);
+    mbar_init(BAR(8), 1);
+    for (int s = 0; s < 8; ++s) { mbar_init(BAR(16 + s), 1); mbar_init(BAR(24 + s), 1); }
     fence_mbar_init();
   }
-  for (int c = threadIdx.x; c < p.Cin; c += NTHREADS) {
-    s_sc[c] = p.in_scale ? p.in_scale[c] : 1.f;
-    s_sh[c] = p.in_scale ? p.in_shift[c] : 0.f;
+  for (int c = threadIdx.x; c < 256; c += NTHREADS) {
+    s_sc[c] = (p.in_scale && c < p.Cin) ? p.in_scale[c] : 1.f;
+    s_sh[c] = (p.in_scale && c < p.Cin) ? p.in_shift[c] : 0.f;
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_ptr), g.tmem_cols);
   tc_fence_before();
@@ -120,146 +151,180 @@ __global__ void __launch_bounds__(NTHREADS) tc_conv_kernel(const TcParams p) {
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
 
-  const long tile0 = (long)blockIdx.x * TILE_M;                  // first virtual position of this tile
   const int taps = p.ks * p.ks;
-  const int center = (p.ks == 3) ? g.Wp + 1 : 0;                 // halo index of tile position 0
+  const int center = (p.ks == 3) ? g.Wp + 1 : 0;                  // halo index of tile position 0
+  const int my_tiles = (int)((g.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
   if (warp == 0) {
-    // ===== TMA producer: weight slabs, in the order the MMA warp consumes them =====
+    // ===== TMA producer: weights =====
     if (lane == 0) {
-      for (int it = 0; it < g.nsteps; ++it) {
-        const int s = it % WSTAGES;
-        mbar_wait(BAR(4 + s), ((it / WSTAGES) & 1) ^ 1);
-        mbar_expect_tx(BAR(s), wslab);
-        tma_bulk_g2s(smem_u32(Wring + (size_t)s * wslab), reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)it * wslab,
-                     wslab, BAR(s));
+      if (g.w_resident) {
+        mbar_expect_tx(BAR(8), (uint32_t)g.wbytes);
+        // bulk copies of <= 32 KB (keeps each request modest; all complete on the same barrier)
+        for (size_t off = 0; off < g.wbytes; off += 32768) {
+          const uint32_t n = (uint32_t)(g.wbytes - off < 32768 ? g.wbytes - off : 32768);
+          tma_bulk_g2s(smem_u32(Wbase + off), reinterpret_cast<const uint8_t*>(p.wpack) + off, n, BAR(8));
+        }
+      } else {
+        long it = 0;
+        for (int ti = 0; ti < my_tiles; ++ti)
+          for (int st = 0; st < g.nsteps; ++st, ++it) {
+            const int s = (int)(it % g.wst);
+            mbar_wait(BAR(24 + s), (uint32_t)(((it / g.wst) & 1) ^ 1));
+            mbar_expect_tx(BAR(16 + s), wslab);
+            tma_bulk_g2s(smem_u32(Wbase + (size_t)s * wslab), reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)st * wslab,
+                         wslab, BAR(16 + s));
+          }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = instr_desc(g.Npad);
-      const uint32_t a_hi0 = smem_u32(A_hi), a_lo0 = smem_u32(A_lo), w0 = smem_u32(Wring);
+      const uint32_t a0 = smem_u32(Abase), w0 = smem_u32(Wbase);
       const uint32_t b_lbo = (uint32_t)g.Npad * 16;
-      int it = 0;
-      for (int grp = 0; grp < g.ngroups; ++grp) {
-        mbar_wait(BAR(8), grp & 1);
+      if (g.w_resident) { mbar_wait(BAR(8), 0); }
+      long it = 0, f = 0;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int as = ti % g.acc_stages;
+        mbar_wait(BAR(6 + as), (uint32_t)(((ti / g.acc_stages) & 1) ^ 1));     // epilogue has drained this accumulator
         tc_fence_after();
-        for (int tap = 0; tap < taps; ++tap) {
-          const int r = tap / p.ks, sft = tap - r * p.ks;
-          const uint32_t pos_off = (p.ks == 3) ? (uint32_t)(r * g.Wp + sft) * 16u : 0u;
-          for (int j = 0; j < g.cg[grp] / 16; ++j, ++it) {
-            const int s = it % WSTAGES;
-            mbar_wait(BAR(s), (it / WSTAGES) & 1);
-            tc_fence_after();
-            const uint32_t aoff = (uint32_t)(2 * j) * plane + pos_off;
-            const uint64_t ah = smem_desc(a_hi0 + aoff, plane, 128), al = smem_desc(a_lo0 + aoff, plane, 128);
-            const uint32_t wb = w0 + (uint32_t)s * wslab;
-            const uint64_t bh = smem_desc(wb, b_lbo, 128), bl = smem_desc(wb + wslab / 2, b_lbo, 128);
-            umma_bf16(tmem, ah, bh, idesc, it > 0 ? 1u : 0u);
-            umma_bf16(tmem, ah, bl, idesc, 1u);
-            umma_bf16(tmem, al, bh, idesc, 1u);
-            umma_commit(BAR(4 + s));                 // ring stage free once these MMAs have read it
-          }
-        }
-        if (grp + 1 < g.ngroups) umma_commit(BAR(9)); // A buffer may be overwritten with the next channel group
-      }
-      umma_commit(BAR(10));                           // accumulator complete
-    }
-  } else {
-    // ===== transform warps (128 threads): gather + BN/ReLU-on-load + bf16 split -> A planes =====
-    const int t = threadIdx.x - 64;
-    const long HpWp = (long)g.Hp * g.Wp;
-    int cbase = 0;
-    for (int grp = 0; grp < g.ngroups; ++grp) {
-      if (grp > 0) mbar_wait(BAR(9), (grp - 1) & 1);
-      const int nchunk = g.cg[grp] / 8;
-      for (int pos = t; pos < g.Lpad; pos += 128) {
-        const long pv = tile0 - center + pos;
-        bool valid = pos < g.L && pv >= 0 && pv < g.Mv;
-        long src = 0;
-        if (valid) {
-          if (p.ks == 3) {
-            const long b = pv / HpWp;
-            const int rem = (int)(pv - b * HpWp);
-            const int row = rem / g.Wp, col = rem - row * g.Wp;
-            valid = row >= 1 && row <= p.H && col >= 1 && col <= p.W;
-            src = ((b * p.H + row - 1) * p.W + (col - 1)) * (long)p.Cin;
-          } else {
-            src = pv * (long)p.Cin;
-          }
-        }
-        const float* xp = p.x + src;
-        for (int c8 = 0; c8 < nchunk; ++c8) {
-          const int c0 = cbase + c8 * 8;
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = 0.f;
-          if (valid && c0 < p.Cin) {
-            if (c0 + 8 <= p.Cin) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 u = __ldg(reinterpret_cast<const float2*>(xp + c0) + i);
-                v[2 * i] = u.x; v[2 * i + 1] = u.y;
+        const uint32_t d = tmem + (uint32_t)(as * g.Npad);
+        int st = 0;
+        for (int grp = 0; grp < g.ngroups; ++grp, ++f) {
+          const int s = (int)(f % g.nastage);
+          mbar_wait(BAR(s), (uint32_t)((f / g.nastage) & 1));
+          tc_fence_after();
+          const uint32_t ab = a0 + (uint32_t)s * (uint32_t)g.a_stage_bytes;
+          for (int tap = 0; tap < taps; ++tap) {
+            const int r = tap / p.ks, sft = tap - r * p.ks;
+            const uint32_t pos_off = (p.ks == 3) ? (uint32_t)(r * g.Wp + sft) * 16u : 0u;
+            for (int j = 0; j < g.cg[grp] / 16; ++j, ++st, ++it) {
+              uint32_t wb;
+              int rs = 0;
+              if (g.w_resident) {
+                wb = w0 + (uint32_t)st * wslab;
+              } else {
+                rs = (int)(it % g.wst);
+                mbar_wait(BAR(16 + rs), (uint32_t)((it / g.wst) & 1));
+                tc_fence_after();
+                wb = w0 + (uint32_t)rs * wslab;
               }
-            } else {
-              for (int i = 0; i < p.Cin - c0; ++i) v[i] = __ldg(xp + c0 + i);
+              const uint32_t aoff = ab + (uint32_t)(2 * j) * plane + pos_off;
+              const uint64_t ah = smem_desc(aoff, plane, 128), al = smem_desc(aoff + lo_off, plane, 128);
+              const uint64_t bh = smem_desc(wb, b_lbo, 128), bl = smem_desc(wb + wslab / 2, b_lbo, 128);
+              umma_bf16(d, ah, bh, idesc, st > 0 ? 1u : 0u);
+              umma_bf16(d, ah, bl, idesc, 1u);
+              umma_bf16(d, al, bh, idesc, 1u);
+              if (!g.w_resident) umma_commit(BAR(24 + rs));
             }
-            if (p.in_scale) {
+          }
+          umma_commit(BAR(2 + s));                      // staged A buffer free
+        }
+        umma_commit(BAR(4 + as));                       // accumulator complete
+      }
+    }
+  } else if (warp < 2 + NTRANS / 32) {
+    // ===== transform warps: gather + BN/ReLU-on-load + bf16 split -> A planes =====
+    const int t = threadIdx.x - 64;
+    long f = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const long tile0 = ((long)blockIdx.x + (long)ti * gridDim.x) * TILE_M;
+      int cbase = 0;
+      for (int grp = 0; grp < g.ngroups; ++grp, ++f) {
+        const int s = (int)(f % g.nastage);
+        mbar_wait(BAR(2 + s), (uint32_t)(((f / g.nastage) & 1) ^ 1));
+        int* src_tab = s_src + s * MAX_LPAD;
+        if (grp == 0 || g.nastage == 1 || true) {
+          for (int pos = t; pos < g.Lpad; pos += NTRANS)
+            src_tab[pos] = (pos < g.L) ? virt_to_pixel(tile0 - center + pos, p) : -1;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NTRANS) : "memory");
+        uint8_t* A_hi = Abase + (size_t)s * g.a_stage_bytes;
+        const int nchunk = g.cg[grp] / 8;
+        const int total = nchunk * g.Lpad;
+        for (int e0 = t; e0 < total; e0 += 2 * NTRANS) {
+          float v[2][8];
+          int posv[2], c8v[2];
+          bool act[2];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (c0 + i < p.Cin) {
-                  float a = fmaf(v[i], s_sc[c0 + i], s_sh[c0 + i]);
-                  v[i] = p.in_relu ? fmaxf(a, 0.f) : a;
+          for (int u = 0; u < 2; ++u) {
+            const int e = e0 + u * NTRANS;
+            act[u] = e < total;
+            const int c8 = act[u] ? e / g.Lpad : 0;
+            const int pos = act[u] ? e - c8 * g.Lpad : 0;
+            posv[u] = pos; c8v[u] = c8;
+            const int c0 = cbase + c8 * 8;
+            const int px = act[u] ? src_tab[pos] : -1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+            if (px >= 0 && c0 < p.Cin) {
+              const float* xp = p.x + (long)px * p.Cin + c0;
+              if (c0 + 8 <= p.Cin) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 w2 = __ldg(reinterpret_cast<const float2*>(xp) + i);
+                  v[u][2 * i] = w2.x; v[u][2 * i + 1] = w2.y;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (c0 + i < p.Cin) v[u][i] = __ldg(xp + i);
+              }
+              if (p.in_scale) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int cc = (c0 + i) & 255;
+                  const float a = fmaf(v[u][i], s_sc[cc], s_sh[cc]);
+                  v[u][i] = (c0 + i < p.Cin) ? (p.in_relu ? fmaxf(a, 0.f) : a) : 0.f;
                 }
               }
             }
           }
-          uint4 hi, lo;
-          split8(v, hi, lo);
-          *reinterpret_cast<uint4*>(A_hi + (size_t)c8 * plane + (size_t)pos * 16) = hi;
-          *reinterpret_cast<uint4*>(A_lo + (size_t)c8 * plane + (size_t)pos * 16) = lo;
-        }
-      }
-      cbase += g.cg[grp];
-      fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      mbar_arrive(BAR(8));
-    }
-    // ===== epilogue: TMEM -> registers -> global (fp32 NHWC), interior positions only =====
-    mbar_wait(BAR(10), 0);
-    tc_fence_after();
-    const int q = warp & 3;                           // TMEM lane quarter this warp may access
-    const int m = q * 32 + lane;
-    const long pv = tile0 + m;
-    bool valid = pv < g.Mv;
-    long dst = 0;
-    if (valid) {
-      if (p.ks == 3) {
-        const long b = pv / HpWp;
-        const int rem = (int)(pv - b * HpWp);
-        const int row = rem / g.Wp, col = rem - row * g.Wp;
-        valid = row >= 1 && row <= p.H && col >= 1 && col <= p.W;
-        dst = ((b * p.H + row - 1) * p.W + (col - 1)) * (long)p.Cout;
-      } else {
-        dst = pv * (long)p.Cout;
-      }
-    }
-    float* yp = p.y + dst;
-    for (int c0 = 0; c0 < g.Npad; c0 += 16) {
-      float v[16];
-      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (valid) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const int c = c0 + i;
-          if (c < p.Cout) {
-            float2 o = make_float2(v[i], v[i + 1]);
-            if (p.bias) { o.x += p.bias[c]; o.y += p.bias[c + 1]; }
-            if (p.accumulate) { const float2 old = *reinterpret_cast<const float2*>(yp + c); o.x += old.x; o.y += old.y; }
-            *reinterpret_cast<float2*>(yp + c) = o;
+          for (int u = 0; u < 2; ++u) {
+            if (act[u]) {
+              uint4 hi, lo;
+              split8(v[u], hi, lo);
+              uint8_t* dst = A_hi + (size_t)c8v[u] * plane + (size_t)posv[u] * 16;
+              *reinterpret_cast<uint4*>(dst) = hi;
+              *reinterpret_cast<uint4*>(dst + lo_off) = lo;
+            }
+          }
+        }
+        cbase += g.cg[grp];
+        fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        mbar_arrive(BAR(s));
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> global (fp32 NHWC), interior positions only =====
+    const int q = warp & 3;                             // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const long tile0 = ((long)blockIdx.x + (long)ti * gridDim.x) * TILE_M;
+      const int as = ti % g.acc_stages;
+      const int px = virt_to_pixel(tile0 + m, p);
+      float* yp = p.y + (long)(px < 0 ? 0 : px) * p.Cout;
+      mbar_wait(BAR(4 + as), (uint32_t)((ti / g.acc_stages) & 1));
+      tc_fence_after();
+      for (int c0 = 0; c0 < g.Npad; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * g.Npad + c0), v);
+        if (px >= 0) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const int c = c0 + i;
+            if (c < p.Cout) {
+              float2 o = make_float2(v[i], v[i + 1]);
+              if (p.bias) { o.x += p.bias[c]; o.y += p.bias[c + 1]; }
+              if (p.accumulate) { const float2 old = *reinterpret_cast<const float2*>(yp + c); o.x += old.x; o.y += old.y; }
+              *reinterpret_cast<float2*>(yp + c) = o;
+            }
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(BAR(6 + as));                         // accumulator stage may be overwritten
     }
   }
   tc_fence_before();
@@ -345,14 +410,13 @@ int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, 
   p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.in_relu = in_relu;
   p.wpack = reinterpret_cast<const __nv_bfloat16*>(wpack); p.bias = bias; p.y = y; p.accumulate = accumulate;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ks = ks;
-  static size_t configured = 0;
-  if (p.g.smem > configured) {
+  static bool configured = false;
+  if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { hcm_set_error("tc_conv: smem attribute: %s", cudaGetErrorString(e)); return HCM_ERR_CUDA; }
-    configured = 227 * 1024;
+    configured = true;
   }
-  const long tiles = (p.g.Mv + TILE_M - 1) / TILE_M;
-  tc_conv_kernel<<<(unsigned)tiles, NTHREADS, p.g.smem, stream>>>(p);
+  tc_conv_kernel<<<(unsigned)p.g.grid, NTHREADS, p.g.smem, stream>>>(p);
   HCM_LAUNCH_CHECK("tc_conv");
   return HCM_OK;
 }
