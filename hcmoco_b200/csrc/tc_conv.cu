@@ -7,18 +7,16 @@
 //
 // Formulation.  The zero-padded input is treated as one flat sequence of "virtual" positions
 // [B][H+2][W+2]; an output tile is 128 consecutive virtual positions, so filter tap (r,s) is nothing
-// but a constant offset r*(W+2)+s in that sequence.  Per tile the CTA
-//   1. (transform warps) gathers the tile's halo once from global memory, applies the producer's
-//      pending BatchNorm scale/shift(+ReLU) on the fly, zeroes padding positions, splits into bf16
-//      hi/lo and stores them channel-chunk-major:  A[chunk(8 ch)][position][16 B]  (hi and lo planes).
-//      In this layout a UMMA K-major/no-swizzle operand for ANY tap is just a different start address
-//      (LBO = plane stride, SBO = 128 B): no im2col copy, every input element is staged once.
-//   2. (TMA warp) streams the pre-packed bf16 hi/lo weight slabs (one per (tap, 16 channels)) through a
-//      4-stage shared-memory ring with cp.async.bulk + mbarrier complete_tx.
-//   3. (MMA warp, one thread) issues tcgen05.mma kind::f16 (bf16 x bf16 -> fp32) M=128, N=ceil16(Cout)
-//      into TMEM, tcgen05.commit releases ring stages / signals the epilogue.
-//   4. (epilogue = the transform warps) tcgen05.ld the accumulator rows, add bias / accumulate, store
-//      the valid (interior) positions as fp32 NHWC.
+// but a constant ROW offset r*(W+2)+s into the staged halo.  Persistent CTAs (one per SM) walk the tiles:
+//   transform warps (256 thr)  gather the tile's halo once from global memory, apply the producer's pending
+//                              BatchNorm scale/shift(+ReLU), zero the padding, split into bf16 hi/lo and store
+//                              them as a swizzled channels-last tile  A[block of 32|64 ch][position][64|128 B]
+//                              (the K-major SWIZZLE_64B/128B UMMA layout; a tap = start row + base_offset);
+//   TMA warp                   weights, pre-packed + pre-swizzled (hi/lo slabs per (tap, channel block)):
+//                              one cp.async.bulk set when they fit in shared memory, else a ring;
+//   MMA warp (one thread)      tcgen05.mma kind::f16 M=128, N=ceil16(Cout), K=16 into a double-buffered TMEM
+//                              accumulator; tcgen05.commit frees A stages / ring slots, signals the epilogue;
+//   epilogue warps (128 thr)   tcgen05.ld, + bias / accumulate, store the interior positions (fp32 NHWC).
 // Outputs computed for padding positions are discarded (waste 2/(W+2) per row).
 #include "tc_common.cuh"
 
@@ -32,10 +30,10 @@ constexpr int HDR_BYTES = 8192;              // barriers, tmem pointer, scale/sh
 constexpr int MAX_LPAD = 512;
 
 struct Geo {
-  int Hp, Wp, L, Lpad, Npad, Cin16, ngroups, cg[MAXG], cgmax, nsteps, tmem_cols;
+  int Hp, Wp, L, Lpad, Npad, Cin16, SW, KB, ngroups, cg[MAXG], cgmax, nblkmax, nslabs, tmem_cols;
   int nastage, acc_stages, w_resident, wst, grid;
   long Mv, tiles;
-  size_t a_stage_bytes, wbytes, smem;
+  size_t plane_bytes, a_stage_bytes, wslab, wbytes, smem;
 };
 
 Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks) {
@@ -45,44 +43,52 @@ Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks) {
   g.Mv = (long)B * g.Hp * g.Wp;
   g.tiles = (g.Mv + TILE_M - 1) / TILE_M;
   g.L = (ks == 3) ? TILE_M + 2 * (g.Wp + 1) : TILE_M;
-  g.Lpad = ceil_to(g.L, 8);
+  g.Lpad = ceil_to(g.L, 16);                 // Lpad * SW is a multiple of 1024 (swizzle pattern period)
   g.Npad = ceil_to(Cout, 16);
   g.Cin16 = ceil_to(Cin, 16);
-  const size_t wslab = (size_t)64 * g.Npad;
-  // channel groups: one staged A buffer holds <= cgmax channels of the halo (hi + lo planes)
-  int max_cg = (int)((72 * 1024) / (4 * g.Lpad)) / 16 * 16;
+  static int force_sw = -1;                   // debug knob: HCM_TC_SW=128 stages every layer with 128-byte rows
+  if (force_sw < 0) { const char* e = getenv("HCM_TC_SW"); force_sw = e ? atoi(e) : 0; }
+  g.SW = (g.Cin16 <= 32 && force_sw != 128) ? 64 : 128;   // bytes per staged row = swizzle span
+  g.KB = g.SW / 2;                           // channels per row block
+  g.plane_bytes = (size_t)g.Lpad * g.SW;
+  g.wslab = (size_t)2 * g.Npad * g.SW;       // hi rows + lo rows of one (tap, channel block)
+  // channel groups: one staged A buffer holds <= max_cg channels of the halo (hi + lo planes)
+  int max_blk = (int)((80 * 1024) / (2 * g.plane_bytes));
+  if (max_blk < 1) max_blk = 1;
+  int max_cg = max_blk * g.KB;
   if (max_cg > 128) max_cg = 128;
-  if (max_cg < 16) max_cg = 16;
   g.ngroups = (g.Cin16 + max_cg - 1) / max_cg;
   int per = ceil_to((g.Cin16 + g.ngroups - 1) / g.ngroups, 16);
   int left = g.Cin16;
   g.cgmax = 0;
-  g.nsteps = 0;
+  g.nslabs = 0;
   for (int i = 0; i < g.ngroups && i < MAXG; ++i) {
     g.cg[i] = left < per ? left : per;
     left -= g.cg[i];
     if (g.cg[i] > g.cgmax) g.cgmax = g.cg[i];
-    g.nsteps += ks * ks * (g.cg[i] / 16);
+    g.nslabs += ks * ks * ((g.cg[i] + g.KB - 1) / g.KB);
   }
-  g.a_stage_bytes = (size_t)4 * g.cgmax * g.Lpad;
+  g.nblkmax = (g.cgmax + g.KB - 1) / g.KB;
+  g.a_stage_bytes = (size_t)2 * g.nblkmax * g.plane_bytes;
   g.acc_stages = (2 * g.Npad <= 512) ? 2 : 1;
   int c = 32;
   while (c < g.acc_stages * g.Npad) c <<= 1;
   g.tmem_cols = c;
-  g.wbytes = (size_t)g.nsteps * wslab;
-  const size_t budget = 220 * 1024 - HDR_BYTES;
-  g.nastage = (2 * g.a_stage_bytes + (g.wbytes < 8 * wslab ? g.wbytes : 8 * wslab) <= budget) ? 2 : 1;
-  const size_t left_b = budget - g.nastage * g.a_stage_bytes;
+  g.wbytes = (size_t)g.nslabs * g.wslab;
+  const size_t budget = 222 * 1024 - HDR_BYTES;
+  const size_t wmin = g.wbytes < 4 * g.wslab ? g.wbytes : 4 * g.wslab;
+  g.nastage = (2 * g.a_stage_bytes + wmin <= budget) ? 2 : 1;
+  const size_t left_b = budget > g.nastage * g.a_stage_bytes ? budget - g.nastage * g.a_stage_bytes : 0;
   g.w_resident = g.wbytes <= left_b ? 1 : 0;
-  g.wst = g.w_resident ? 0 : (int)(left_b / wslab > 8 ? 8 : left_b / wslab);
-  g.smem = HDR_BYTES + g.nastage * g.a_stage_bytes + (g.w_resident ? g.wbytes : (size_t)g.wst * wslab);
+  g.wst = g.w_resident ? 0 : (int)(left_b / g.wslab > 8 ? 8 : left_b / g.wslab);
+  g.smem = HDR_BYTES + g.nastage * g.a_stage_bytes + (g.w_resident ? g.wbytes : (size_t)g.wst * g.wslab);
   g.grid = (int)(g.tiles < 148 ? g.tiles : 148);
   return g;
 }
 
 bool geo_ok(const Geo& g, int Cin, int Cout, int ks) {
   return (ks == 1 || ks == 3) && Cin <= 256 && Cout <= 256 && (Cout % 2) == 0 && (Cin % 2) == 0 && g.ngroups <= MAXG &&
-         g.Lpad <= MAX_LPAD && g.Mv < (1L << 31) && (g.w_resident || g.wst >= 2) && g.smem <= 225 * 1024;
+         g.Lpad <= MAX_LPAD && g.Mv < (1L << 31) && (g.w_resident || g.wst >= 2) && g.smem <= 226 * 1024;
 }
 
 struct TcParams {
@@ -95,6 +101,7 @@ struct TcParams {
   float* y;
   int accumulate;
   int B, H, W, Cin, Cout, ks;
+  int base_offset_mode;        // 1: descriptor base_offset = (start >> 7) & 7 (row-shifted swizzled operands)
   Geo g;
 };
 
@@ -110,9 +117,25 @@ __device__ __forceinline__ int virt_to_pixel(long pv, const TcParams& p) {
   return (int)((b * p.H + row - 1) * p.W + (col - 1));
 }
 
+// byte offset of 16-byte chunk `c16` of row `row` inside a swizzled plane (rows of SW bytes, 1024-B aligned base):
+// Swizzle<log2(SW/16),4,3>: the chunk index is XORed with address bits [7, 7+log2(SW/16))
+__host__ __device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t c16, uint32_t SW) {
+  const uint32_t off = row * SW;
+  return off + (((c16 ^ (off >> 7)) & (SW / 16 - 1)) << 4);
+}
+
+// K-major swizzled operand descriptor: rows of SW bytes, 8-row groups SBO = 8*SW apart
+__device__ __forceinline__ uint64_t sw_desc(uint32_t saddr, uint32_t SW, int base_offset_mode) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                                   // LBO (unused for swizzled K-major; CUTLASS writes 1)
+  d |= (uint64_t)(((8 * SW) >> 4) & 0x3FFFu) << 32;         // SBO
+  d |= (uint64_t)1 << 46;                                   // descriptor version (sm_100)
+  if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  d |= (uint64_t)(SW == 128 ? 2 : (SW == 64 ? 4 : 6)) << 61;
+  return d;
+}
+
 // ------------------------------------------------------------------------------------------ the kernel
-// Persistent: CTA b owns tiles b, b+grid, ...  Pipelines: staged A buffers (transform <-> MMA), TMEM accumulator
-// stages (MMA <-> epilogue), weights resident in shared memory (one bulk copy) or streamed through a ring.
 __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Geo& g = p.g;
@@ -123,10 +146,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
   float* s_sh = s_sc + 256;
   int* s_src = reinterpret_cast<int*>(smem + 3072);               // [2][MAX_LPAD]
   uint8_t* Abase = smem + HDR_BYTES;
-  const uint32_t plane = (uint32_t)g.Lpad * 16;
-  const uint32_t lo_off = (uint32_t)(g.cgmax / 8) * plane;        // A_lo planes follow the A_hi planes of a stage
+  const uint32_t SW = (uint32_t)g.SW;
+  const uint32_t plane = (uint32_t)g.plane_bytes;
+  const uint32_t lo_off = (uint32_t)g.nblkmax * plane;            // A_lo planes follow the A_hi planes of a stage
   uint8_t* Wbase = Abase + (size_t)g.nastage * g.a_stage_bytes;
-  const uint32_t wslab = 64u * g.Npad;
+  const uint32_t wslab = (uint32_t)g.wslab;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -152,7 +176,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
   const uint32_t tmem = *tmem_ptr;
 
   const int taps = p.ks * p.ks;
-  const int center = (p.ks == 3) ? g.Wp + 1 : 0;                  // halo index of tile position 0
+  const int center = (p.ks == 3) ? g.Wp + 1 : 0;                  // halo row of tile position 0
   const int my_tiles = (int)((g.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
   if (warp == 0) {
@@ -160,7 +184,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     if (lane == 0) {
       if (g.w_resident) {
         mbar_expect_tx(BAR(8), (uint32_t)g.wbytes);
-        // bulk copies of <= 32 KB (keeps each request modest; all complete on the same barrier)
         for (size_t off = 0; off < g.wbytes; off += 32768) {
           const uint32_t n = (uint32_t)(g.wbytes - off < 32768 ? g.wbytes - off : 32768);
           tma_bulk_g2s(smem_u32(Wbase + off), reinterpret_cast<const uint8_t*>(p.wpack) + off, n, BAR(8));
@@ -168,11 +191,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
       } else {
         long it = 0;
         for (int ti = 0; ti < my_tiles; ++ti)
-          for (int st = 0; st < g.nsteps; ++st, ++it) {
+          for (int sl = 0; sl < g.nslabs; ++sl, ++it) {
             const int s = (int)(it % g.wst);
             mbar_wait(BAR(24 + s), (uint32_t)(((it / g.wst) & 1) ^ 1));
             mbar_expect_tx(BAR(16 + s), wslab);
-            tma_bulk_g2s(smem_u32(Wbase + (size_t)s * wslab), reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)st * wslab,
+            tma_bulk_g2s(smem_u32(Wbase + (size_t)s * wslab), reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)sl * wslab,
                          wslab, BAR(16 + s));
           }
       }
@@ -182,7 +205,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     if (lane == 0) {
       const uint32_t idesc = instr_desc(g.Npad);
       const uint32_t a0 = smem_u32(Abase), w0 = smem_u32(Wbase);
-      const uint32_t b_lbo = (uint32_t)g.Npad * 16;
       if (g.w_resident) { mbar_wait(BAR(8), 0); }
       long it = 0, f = 0;
       for (int ti = 0; ti < my_tiles; ++ti) {
@@ -190,32 +212,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
         mbar_wait(BAR(6 + as), (uint32_t)(((ti / g.acc_stages) & 1) ^ 1));     // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d = tmem + (uint32_t)(as * g.Npad);
-        int st = 0;
+        int sl = 0;
+        uint32_t first = 1;
         for (int grp = 0; grp < g.ngroups; ++grp, ++f) {
           const int s = (int)(f % g.nastage);
           mbar_wait(BAR(s), (uint32_t)((f / g.nastage) & 1));
           tc_fence_after();
           const uint32_t ab = a0 + (uint32_t)s * (uint32_t)g.a_stage_bytes;
+          const int nblk = (g.cg[grp] + g.KB - 1) / g.KB;
           for (int tap = 0; tap < taps; ++tap) {
             const int r = tap / p.ks, sft = tap - r * p.ks;
-            const uint32_t pos_off = (p.ks == 3) ? (uint32_t)(r * g.Wp + sft) * 16u : 0u;
-            for (int j = 0; j < g.cg[grp] / 16; ++j, ++st, ++it) {
+            const uint32_t row_off = (p.ks == 3) ? (uint32_t)(r * g.Wp + sft) * SW : 0u;
+            for (int blk = 0; blk < nblk; ++blk, ++sl, ++it) {
               uint32_t wb;
               int rs = 0;
               if (g.w_resident) {
-                wb = w0 + (uint32_t)st * wslab;
+                wb = w0 + (uint32_t)sl * wslab;
               } else {
                 rs = (int)(it % g.wst);
                 mbar_wait(BAR(16 + rs), (uint32_t)((it / g.wst) & 1));
                 tc_fence_after();
                 wb = w0 + (uint32_t)rs * wslab;
               }
-              const uint32_t aoff = ab + (uint32_t)(2 * j) * plane + pos_off;
-              const uint64_t ah = smem_desc(aoff, plane, 128), al = smem_desc(aoff + lo_off, plane, 128);
-              const uint64_t bh = smem_desc(wb, b_lbo, 128), bl = smem_desc(wb + wslab / 2, b_lbo, 128);
-              umma_bf16(d, ah, bh, idesc, st > 0 ? 1u : 0u);
-              umma_bf16(d, ah, bl, idesc, 1u);
-              umma_bf16(d, al, bh, idesc, 1u);
+              const int ksteps = min(g.KB, g.cg[grp] - blk * g.KB) / 16;
+              const uint32_t arow = ab + (uint32_t)blk * plane + row_off;
+              for (int j = 0; j < ksteps; ++j) {
+                const uint64_t ah = sw_desc(arow + 32u * j, SW, p.base_offset_mode);
+                const uint64_t al = sw_desc(arow + lo_off + 32u * j, SW, p.base_offset_mode);
+                const uint64_t bh = sw_desc(wb + 32u * j, SW, 0), bl = sw_desc(wb + wslab / 2 + 32u * j, SW, 0);
+                umma_bf16(d, ah, bh, idesc, first ? 0u : 1u);
+                first = 0;
+                umma_bf16(d, ah, bl, idesc, 1u);
+                umma_bf16(d, al, bh, idesc, 1u);
+              }
               if (!g.w_resident) umma_commit(BAR(24 + rs));
             }
           }
@@ -225,8 +254,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
       }
     }
   } else if (warp < 2 + NTRANS / 32) {
-    // ===== transform warps: gather + BN/ReLU-on-load + bf16 split -> A planes =====
+    // ===== transform warps: gather + BN/ReLU-on-load + bf16 split -> swizzled channels-last tile =====
     const int t = threadIdx.x - 64;
+    const uint32_t cpb = SW / 16;                       // 16-byte chunks per row block
     long f = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
       const long tile0 = ((long)blockIdx.x + (long)ti * gridDim.x) * TILE_M;
@@ -235,17 +265,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
         const int s = (int)(f % g.nastage);
         mbar_wait(BAR(2 + s), (uint32_t)(((f / g.nastage) & 1) ^ 1));
         int* src_tab = s_src + s * MAX_LPAD;
-        if (grp == 0 || g.nastage == 1 || true) {
-          for (int pos = t; pos < g.Lpad; pos += NTRANS)
-            src_tab[pos] = (pos < g.L) ? virt_to_pixel(tile0 - center + pos, p) : -1;
-        }
+        for (int pos = t; pos < g.Lpad; pos += NTRANS)
+          src_tab[pos] = (pos < g.L) ? virt_to_pixel(tile0 - center + pos, p) : -1;
         asm volatile("bar.sync 1, %0;" ::"n"(NTRANS) : "memory");
         uint8_t* A_hi = Abase + (size_t)s * g.a_stage_bytes;
         const int nchunk = g.cg[grp] / 8;
         const int total = nchunk * g.Lpad;
         for (int e0 = t; e0 < total; e0 += 2 * NTRANS) {
           float v[2][8];
-          int posv[2], c8v[2];
+          uint32_t dstoff[2];
           bool act[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
@@ -253,7 +281,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
             act[u] = e < total;
             const int c8 = act[u] ? e / g.Lpad : 0;
             const int pos = act[u] ? e - c8 * g.Lpad : 0;
-            posv[u] = pos; c8v[u] = c8;
+            dstoff[u] = (uint32_t)(c8 / cpb) * plane + swz((uint32_t)pos, (uint32_t)c8 % cpb, SW);
             const int c0 = cbase + c8 * 8;
             const int px = act[u] ? src_tab[pos] : -1;
 #pragma unroll
@@ -285,9 +313,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
             if (act[u]) {
               uint4 hi, lo;
               split8(v[u], hi, lo);
-              uint8_t* dst = A_hi + (size_t)c8v[u] * plane + (size_t)posv[u] * 16;
-              *reinterpret_cast<uint4*>(dst) = hi;
-              *reinterpret_cast<uint4*>(dst + lo_off) = lo;
+              *reinterpret_cast<uint4*>(A_hi + dstoff[u]) = hi;
+              *reinterpret_cast<uint4*>(A_hi + lo_off + dstoff[u]) = lo;
             }
           }
         }
@@ -333,37 +360,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
 }
 
 // ------------------------------------------------------------------------------------------ weight packing
-// wpack: for every K step (channel group, tap, 16 channels) one slab of 64*Npad bytes:
-//   hi[2 chunks][Npad][8 bf16], lo[2 chunks][Npad][8 bf16]   (the shared-memory image of the B operand)
+// wpack: one slab per (channel group, tap, channel block of KB = SW/2 channels):
+//   hi[Npad rows][SW bytes], lo[Npad rows][SW bytes]   — the swizzled shared-memory image of the K-major B operand
 // transpose = 0: B[n][c] = w[n][c][tap]                        (forward; w is OIHW [Cout][Cin][ks][ks])
 // transpose = 1: B[n][c] = w[c][n][taps-1-tap]  with the conv seen from the gradient side:
 //                n runs over the ORIGINAL Cin, c over the ORIGINAL Cout (data gradient)
-__global__ void tc_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, Geo g, int Cin, int Cout, int ks,
+__global__ void tc_pack_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, Geo g, int Cin, int Cout, int ks,
                                int transpose, int wCin) {
   const int taps = ks * ks;
-  const long total = (long)g.nsteps * 2 * g.Npad * 8;            // (step, chunk, n, k) tuples; hi and lo written together
+  const long total = (long)g.nslabs * g.Npad * g.KB;             // (slab, n, k) tuples; hi and lo written together
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const int k = (int)(e & 7);
-    long r = e >> 3;
-    const int n = (int)(r % g.Npad); r /= g.Npad;
-    const int h = (int)(r & 1);
-    int step = (int)(r >> 1);
-    // decode step -> (group, tap, j)
-    int grp = 0, cbase = 0, st = step;
-    while (st >= taps * (g.cg[grp] / 16)) { st -= taps * (g.cg[grp] / 16); cbase += g.cg[grp]; ++grp; }
-    const int tap = st / (g.cg[grp] / 16), j = st - tap * (g.cg[grp] / 16);
-    const int c = cbase + j * 16 + h * 8 + k;
+    const int k = (int)(e % g.KB);
+    long r = e / g.KB;
+    const int n = (int)(r % g.Npad);
+    int sl = (int)(r / g.Npad);
+    // decode slab -> (group, tap, block)
+    int grp = 0, cbase = 0, st = sl;
+    for (;;) {
+      const int nb = (g.cg[grp] + g.KB - 1) / g.KB;
+      if (st < taps * nb) break;
+      st -= taps * nb; cbase += g.cg[grp]; ++grp;
+    }
+    const int nb = (g.cg[grp] + g.KB - 1) / g.KB;
+    const int tap = st / nb, blk = st - tap * nb;
+    const int cl = blk * g.KB + k;                                // channel within the group
+    const int c = cbase + cl;
     float v = 0.f;
-    if (n < Cout && c < Cin) {
+    if (n < Cout && c < Cin && cl < g.cg[grp]) {
       v = transpose ? w[((long)c * wCin + n) * taps + (taps - 1 - tap)] : w[((long)n * wCin + c) * taps + tap];
     }
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    __nv_bfloat16* slab = out + (long)step * 32 * g.Npad;
-    slab[((long)h * g.Npad + n) * 8 + k] = hi;
-    slab[(long)16 * g.Npad + ((long)h * g.Npad + n) * 8 + k] = lo;
+    uint8_t* slab = out + (size_t)sl * g.wslab;
+    const uint32_t off = swz((uint32_t)n, (uint32_t)(k >> 3), (uint32_t)g.SW) + (uint32_t)(k & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(slab + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(slab + g.wslab / 2 + off) = lo;
   }
 }
+
+int g_base_offset_mode = -1;
 
 }  // namespace
 
@@ -379,10 +414,10 @@ int hcm_tc_conv_supported(int B, int H, int W, int Cin, int Cout, int ks, int st
 // bytes of the packed-weight buffer for this geometry
 long hcm_tc_conv_wpack_bytes(int B, int H, int W, int Cin, int Cout, int ks) {
   Geo g = make_geo(B, H, W, Cin, Cout, ks);
-  return (long)g.nsteps * 64 * g.Npad;
+  return (long)g.wbytes;
 }
 
-// Pack OIHW fp32 weights into the bf16 hi/lo K-step slabs.  (Cin, Cout) describe the GEMM being run:
+// Pack OIHW fp32 weights into the bf16 hi/lo slabs.  (Cin, Cout) describe the GEMM being run:
 // transpose=0 -> the forward conv of w[Cout][Cin][ks][ks];  transpose=1 -> its data gradient, i.e. a conv with
 // Cin' = Cout(w), Cout' = Cin(w): pass Cin = Cout(w), Cout = Cin(w).
 int hcm_tc_conv_pack(const float* w, void* wpack, int B, int H, int W, int Cin, int Cout, int ks, int transpose,
@@ -390,11 +425,11 @@ int hcm_tc_conv_pack(const float* w, void* wpack, int B, int H, int W, int Cin, 
   HCM_CHECK_ARG(w && wpack, "tc_conv_pack: null pointer");
   Geo g = make_geo(B, H, W, Cin, Cout, ks);
   HCM_CHECK_ARG(geo_ok(g, Cin, Cout, ks), "tc_conv_pack: unsupported geometry");
-  const long total = (long)g.nsteps * 2 * g.Npad * 8;
+  const long total = (long)g.nslabs * g.Npad * g.KB;
   const int wCin = transpose ? Cout : Cin;                       // inner (second) dimension of the OIHW tensor
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  tc_pack_kernel<<<grid, 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(wpack), g, Cin, Cout, ks, transpose, wCin);
+  tc_pack_kernel<<<grid, 256, 0, stream>>>(w, reinterpret_cast<uint8_t*>(wpack), g, Cin, Cout, ks, transpose, wCin);
   HCM_LAUNCH_CHECK("tc_conv_pack");
   return HCM_OK;
 }
@@ -410,6 +445,11 @@ int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, 
   p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.in_relu = in_relu;
   p.wpack = reinterpret_cast<const __nv_bfloat16*>(wpack); p.bias = bias; p.y = y; p.accumulate = accumulate;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ks = ks;
+  if (g_base_offset_mode < 0) {
+    const char* e = getenv("HCM_TC_BASE_OFFSET");
+    g_base_offset_mode = e ? atoi(e) : 1;
+  }
+  p.base_offset_mode = g_base_offset_mode;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
