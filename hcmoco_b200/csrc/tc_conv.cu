@@ -31,7 +31,7 @@ constexpr int MAX_LPAD = 512;
 
 struct Geo {
   int Hp, Wp, L, Lpad, Npad, Cin16, SW, KB, ngroups, cg[MAXG], cgmax, nblkmax, nslabs, tmem_cols;
-  int nastage, acc_stages, w_resident, wst, grid;
+  int nastage, acc_stages, nacc, w_resident, wst, grid;
   long Mv, tiles;
   size_t plane_bytes, a_stage_bytes, wslab, wbytes, smem;
 };
@@ -70,9 +70,12 @@ Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks) {
   }
   g.nblkmax = (g.cgmax + g.KB - 1) / g.KB;
   g.a_stage_bytes = (size_t)2 * g.nblkmax * g.plane_bytes;
-  g.acc_stages = (2 * g.Npad <= 512) ? 2 : 1;
+  // independent TMEM accumulators for the split-precision passes (hi*hi | hi*lo | lo*hi): back-to-back MMAs into the
+  // SAME accumulator serialise on its read-modify-write latency (~250 cycles measured at N<=64); the epilogue adds them
+  g.nacc = (3 * g.Npad <= 512) ? 3 : 2;
+  g.acc_stages = (2 * g.nacc * g.Npad <= 512) ? 2 : 1;
   int c = 32;
-  while (c < g.acc_stages * g.Npad) c <<= 1;
+  while (c < g.acc_stages * g.nacc * g.Npad) c <<= 1;
   g.tmem_cols = c;
   g.wbytes = (size_t)g.nslabs * g.wslab;
   const size_t budget = 222 * 1024 - HDR_BYTES;
@@ -211,7 +214,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
         const int as = ti % g.acc_stages;
         mbar_wait(BAR(6 + as), (uint32_t)(((ti / g.acc_stages) & 1) ^ 1));     // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d = tmem + (uint32_t)(as * g.Npad);
+        const uint32_t d0 = tmem + (uint32_t)(as * g.nacc * g.Npad);
+        const uint32_t d1 = d0 + (uint32_t)g.Npad, d2 = d0 + (uint32_t)((g.nacc - 1) * g.Npad);
         int sl = 0;
         uint32_t first = 1;
         for (int grp = 0; grp < g.ngroups; ++grp, ++f) {
@@ -240,10 +244,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
                 const uint64_t ah = sw_desc(arow + 32u * j, SW, p.base_offset_mode);
                 const uint64_t al = sw_desc(arow + lo_off + 32u * j, SW, p.base_offset_mode);
                 const uint64_t bh = sw_desc(wb + 32u * j, SW, 0), bl = sw_desc(wb + wslab / 2 + 32u * j, SW, 0);
-                umma_bf16(d, ah, bh, idesc, first ? 0u : 1u);
+                umma_bf16(d0, ah, bh, idesc, first ? 0u : 1u);
+                umma_bf16(d1, ah, bl, idesc, first ? 0u : 1u);
+                umma_bf16(d2, al, bh, idesc, (first && g.nacc == 3) ? 0u : 1u);
                 first = 0;
-                umma_bf16(d, ah, bl, idesc, 1u);
-                umma_bf16(d, al, bh, idesc, 1u);
               }
               if (!g.w_resident) umma_commit(BAR(24 + rs));
             }
@@ -336,7 +340,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
       tc_fence_after();
       for (int c0 = 0; c0 < g.Npad; c0 += 16) {
         float v[16];
-        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * g.Npad + c0), v);
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * g.nacc * g.Npad + c0);
+        tmem_ld16(tbase, v);
+        for (int a = 1; a < g.nacc; ++a) {
+          float u[16];
+          tmem_ld16(tbase + (uint32_t)(a * g.Npad), u);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += u[i];
+        }
         if (px >= 0) {
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
@@ -447,7 +458,7 @@ int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, 
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ks = ks;
   if (g_base_offset_mode < 0) {
     const char* e = getenv("HCM_TC_BASE_OFFSET");
-    g_base_offset_mode = e ? atoi(e) : 1;
+    g_base_offset_mode = e ? atoi(e) : 0;   // measured on B200: the swizzle XOR uses absolute smem address bits
   }
   p.base_offset_mode = g_base_offset_mode;
   static bool configured = false;
