@@ -23,8 +23,10 @@
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int NTRANS = 256;                  // transform threads: warps 2..9
-constexpr int NTHREADS = 64 + NTRANS + 128;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 10..13: epilogue
+constexpr int NTRANS = 256;                  // transform threads: warps 0..7
+constexpr int NTHREADS = NTRANS + 128 + 64;  // warps 8..11: epilogue, warp 12: TMA producer, warp 13: MMA issuer + TMEM owner
+// (the SMSP arbiter favours the highest warp id: the single MMA-issuing thread must not starve behind busy transform warps)
+constexpr int W_EPI = NTRANS / 32, W_TMA = W_EPI + 4, W_MMA = W_TMA + 1;
 constexpr int MAXG = 8;
 constexpr int HDR_BYTES = 8192;              // barriers, tmem pointer, scale/shift (2 x 256 floats), position tables (2 x 512 int)
 constexpr int MAX_LPAD = 512;
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     s_sc[c] = (p.in_scale && c < p.Cin) ? p.in_scale[c] : 1.f;
     s_sh[c] = (p.in_scale && c < p.Cin) ? p.in_shift[c] : 0.f;
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr), g.tmem_cols);
+  if (warp == W_MMA) tmem_alloc(smem_u32(tmem_ptr), g.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
   const int center = (p.ks == 3) ? g.Wp + 1 : 0;                  // halo row of tile position 0
   const int my_tiles = (int)((g.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     // ===== TMA producer: weights =====
     if (lane == 0) {
       if (g.w_resident) {
@@ -203,11 +205,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
           }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = instr_desc(g.Npad);
       const uint32_t a0 = smem_u32(Abase), w0 = smem_u32(Wbase);
+      const uint64_t desc_t = sw_desc(0, SW, 0);        // everything but the start-address field
       if (g.w_resident) { mbar_wait(BAR(8), 0); }
       long it = 0, f = 0;
       for (int ti = 0; ti < my_tiles; ++ti) {
@@ -241,9 +244,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
               const int ksteps = min(g.KB, g.cg[grp] - blk * g.KB) / 16;
               const uint32_t arow = ab + (uint32_t)blk * plane + row_off;
               for (int j = 0; j < ksteps; ++j) {
-                const uint64_t ah = sw_desc(arow + 32u * j, SW, p.base_offset_mode);
-                const uint64_t al = sw_desc(arow + lo_off + 32u * j, SW, p.base_offset_mode);
-                const uint64_t bh = sw_desc(wb + 32u * j, SW, 0), bl = sw_desc(wb + wslab / 2 + 32u * j, SW, 0);
+                const uint64_t ah = desc_t | (uint64_t)(((arow + 32u * j) & 0x3FFFFu) >> 4);
+                const uint64_t al = desc_t | (uint64_t)(((arow + lo_off + 32u * j) & 0x3FFFFu) >> 4);
+                const uint64_t bh = desc_t | (uint64_t)(((wb + 32u * j) & 0x3FFFFu) >> 4);
+                const uint64_t bl = desc_t | (uint64_t)(((wb + wslab / 2 + 32u * j) & 0x3FFFFu) >> 4);
                 umma_bf16(d0, ah, bh, idesc, first ? 0u : 1u);
                 umma_bf16(d1, ah, bl, idesc, first ? 0u : 1u);
                 umma_bf16(d2, al, bh, idesc, (first && g.nacc == 3) ? 0u : 1u);
@@ -257,9 +261,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
         umma_commit(BAR(4 + as));                       // accumulator complete
       }
     }
-  } else if (warp < 2 + NTRANS / 32) {
+  } else if (warp < W_EPI) {
     // ===== transform warps: gather + BN/ReLU-on-load + bf16 split -> swizzled channels-last tile =====
-    const int t = threadIdx.x - 64;
+    const int t = threadIdx.x;
     const uint32_t cpb = SW / 16;                       // 16-byte chunks per row block
     long f = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, g.tmem_cols);
+  if (warp == W_MMA) tmem_dealloc(tmem, g.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------ weight packing
