@@ -106,6 +106,7 @@ struct TcParams {
   float* y;
   int accumulate;
   int B, H, W, Cin, Cout, ks;
+  long long* dbg;              // optional per-CTA cycle counters (HCM_TC_DEBUG), else null
   int base_offset_mode;        // 1: descriptor base_offset = (start >> 7) & 7 (row-shifted swizzled operands)
   Geo g;
 };
@@ -206,16 +207,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
       }
     }
   } else if (warp == W_MMA) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues tcgen05 =====
+    {
       const uint32_t idesc = instr_desc(g.Npad);
       const uint32_t a0 = smem_u32(Abase), w0 = smem_u32(Wbase);
       const uint64_t desc_t = sw_desc(0, SW, 0);        // everything but the start-address field
+      long long c_w = 0, c_acc = 0, c_a = 0, c_all = clock64(), tq;
+      tq = clock64();
       if (g.w_resident) { mbar_wait(BAR(8), 0); }
+      c_w += clock64() - tq;
       long it = 0, f = 0;
       for (int ti = 0; ti < my_tiles; ++ti) {
         const int as = ti % g.acc_stages;
+        tq = clock64();
         mbar_wait(BAR(6 + as), (uint32_t)(((ti / g.acc_stages) & 1) ^ 1));     // epilogue has drained this accumulator
+        c_acc += clock64() - tq;
         tc_fence_after();
         const uint32_t d0 = tmem + (uint32_t)(as * g.nacc * g.Npad);
         const uint32_t d1 = d0 + (uint32_t)g.Npad, d2 = d0 + (uint32_t)((g.nacc - 1) * g.Npad);
@@ -223,7 +229,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
         uint32_t first = 1;
         for (int grp = 0; grp < g.ngroups; ++grp, ++f) {
           const int s = (int)(f % g.nastage);
+          tq = clock64();
           mbar_wait(BAR(s), (uint32_t)((f / g.nastage) & 1));
+          c_a += clock64() - tq;
           tc_fence_after();
           const uint32_t ab = a0 + (uint32_t)s * (uint32_t)g.a_stage_bytes;
           const int nblk = (g.cg[grp] + g.KB - 1) / g.KB;
@@ -248,17 +256,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
                 const uint64_t al = desc_t | (uint64_t)(((arow + lo_off + 32u * j) & 0x3FFFFu) >> 4);
                 const uint64_t bh = desc_t | (uint64_t)(((wb + 32u * j) & 0x3FFFFu) >> 4);
                 const uint64_t bl = desc_t | (uint64_t)(((wb + wslab / 2 + 32u * j) & 0x3FFFFu) >> 4);
-                umma_bf16(d0, ah, bh, idesc, first ? 0u : 1u);
-                umma_bf16(d1, ah, bl, idesc, first ? 0u : 1u);
-                umma_bf16(d2, al, bh, idesc, (first && g.nacc == 3) ? 0u : 1u);
+                if (elect_one()) {
+                  umma_bf16(d0, ah, bh, idesc, first ? 0u : 1u);
+                  umma_bf16(d1, ah, bl, idesc, first ? 0u : 1u);
+                  umma_bf16(d2, al, bh, idesc, (first && g.nacc == 3) ? 0u : 1u);
+                }
                 first = 0;
               }
-              if (!g.w_resident) umma_commit(BAR(24 + rs));
+              if (!g.w_resident && elect_one()) umma_commit(BAR(24 + rs));
             }
           }
-          umma_commit(BAR(2 + s));                      // staged A buffer free
+          if (elect_one()) umma_commit(BAR(2 + s));     // staged A buffer free
         }
-        umma_commit(BAR(4 + as));                       // accumulator complete
+        if (elect_one()) umma_commit(BAR(4 + as));      // accumulator complete
+      }
+      if (p.dbg && lane == 0) {
+        long long* o = p.dbg + (long)blockIdx.x * 16;
+        o[0] = clock64() - c_all; o[1] = c_w; o[2] = c_acc; o[3] = c_a;
       }
     }
   } else if (warp < W_EPI) {
@@ -266,12 +280,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     const int t = threadIdx.x;
     const uint32_t cpb = SW / 16;                       // 16-byte chunks per row block
     long f = 0;
+    long long c_wait = 0, c_all = clock64(), tq;
     for (int ti = 0; ti < my_tiles; ++ti) {
       const long tile0 = ((long)blockIdx.x + (long)ti * gridDim.x) * TILE_M;
       int cbase = 0;
       for (int grp = 0; grp < g.ngroups; ++grp, ++f) {
         const int s = (int)(f % g.nastage);
+        tq = clock64();
         mbar_wait(BAR(2 + s), (uint32_t)(((f / g.nastage) & 1) ^ 1));
+        c_wait += clock64() - tq;
         int* src_tab = s_src + s * MAX_LPAD;
         for (int pos = t; pos < g.Lpad; pos += NTRANS)
           src_tab[pos] = (pos < g.L) ? virt_to_pixel(tile0 - center + pos, p) : -1;
@@ -331,16 +348,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
         mbar_arrive(BAR(s));
       }
     }
+    if (p.dbg && t == 0) { long long* o = p.dbg + (long)blockIdx.x * 16; o[4] = clock64() - c_all; o[5] = c_wait; }
   } else {
     // ===== epilogue warps: TMEM -> registers -> global (fp32 NHWC), interior positions only =====
     const int q = warp & 3;                             // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
+    long long c_wait = 0, c_all = clock64(), tq;
     for (int ti = 0; ti < my_tiles; ++ti) {
       const long tile0 = ((long)blockIdx.x + (long)ti * gridDim.x) * TILE_M;
       const int as = ti % g.acc_stages;
       const int px = virt_to_pixel(tile0 + m, p);
       float* yp = p.y + (long)(px < 0 ? 0 : px) * p.Cout;
+      tq = clock64();
       mbar_wait(BAR(4 + as), (uint32_t)((ti / g.acc_stages) & 1));
+      c_wait += clock64() - tq;
       tc_fence_after();
       for (int c0 = 0; c0 < g.Npad; c0 += 16) {
         float v[16];
@@ -368,6 +389,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
       tc_fence_before();
       mbar_arrive(BAR(6 + as));                         // accumulator stage may be overwritten
     }
+    if (p.dbg && m == 0) { long long* o = p.dbg + (long)blockIdx.x * 16; o[6] = clock64() - c_all; o[7] = c_wait; }
   }
   tc_fence_before();
   __syncthreads();
@@ -465,6 +487,14 @@ int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, 
     g_base_offset_mode = e ? atoi(e) : 0;   // measured on B200: the swizzle XOR uses absolute smem address bits
   }
   p.base_offset_mode = g_base_offset_mode;
+  static long long* dbg = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    dbg_on = getenv("HCM_TC_DEBUG") ? 1 : 0;
+    if (dbg_on) cudaMalloc(&dbg, 148 * 16 * sizeof(long long));
+  }
+  p.dbg = dbg;
+  if (dbg_on) cudaMemsetAsync(dbg, 0, 148 * 16 * sizeof(long long), stream);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -473,6 +503,14 @@ int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, 
   }
   tc_conv_kernel<<<(unsigned)p.g.grid, NTHREADS, p.g.smem, stream>>>(p);
   HCM_LAUNCH_CHECK("tc_conv");
+  if (dbg_on) {
+    long long h[148 * 16];
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long* o = h;      // CTA 0
+    fprintf(stderr, "[tc_conv dbg] %dx%d %d->%d k%d tiles/cta %ld | mma: total %lld wait_w %lld wait_acc %lld wait_a %lld | "
+            "transform: total %lld wait %lld | epilogue: total %lld wait %lld\n", H, W, Cin, Cout, ks,
+            (p.g.tiles + p.g.grid - 1) / p.g.grid, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+  }
   return HCM_OK;
 }
 
