@@ -163,9 +163,14 @@ __global__ void __launch_bounds__(NCE_THREADS) nce_bwd_kernel(const NceArgs a, c
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane >> 3, l8 = lane & 7;
+  // lse == nullptr: `logits` already holds d(loss)/d(logits) (generic autograd backward of the logits-returning API)
+  const bool generic = (lse == nullptr);
   float cf[6], ls[6];
 #pragma unroll
-  for (int q = 0; q < 6; ++q) { cf[q] = coef[q * a.B + b] * a.invT * gscale; ls[q] = lse[q * a.B + b]; }
+  for (int q = 0; q < 6; ++q) {
+    cf[q] = (generic ? 1.f : coef[q * a.B + b]) * a.invT * gscale;
+    ls[q] = generic ? 0.f : lse[q * a.B + b];
+  }
   float4 acc[3][4];
 #pragma unroll
   for (int m = 0; m < 3; ++m)
@@ -186,8 +191,8 @@ __global__ void __launch_bounds__(NCE_THREADS) nce_bwd_kernel(const NceArgs a, c
     float s[6];
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
-      const float lg = valid ? logits[((long)q * a.B + b) * a.K1 + k] : -INFINITY;
-      s[q] = valid ? cf[q] * (__expf(lg - ls[q]) - ((k == 0) ? 1.f : 0.f)) : 0.f;
+      const float lg = valid ? logits[((long)q * a.B + b) * a.K1 + k] : (generic ? 0.f : -INFINITY);
+      s[q] = !valid ? 0.f : (generic ? cf[q] * lg : cf[q] * (__expf(lg - ls[q]) - ((k == 0) ? 1.f : 0.f)));
     }
     // dx1 <- pairs 0 (w2), 4 (w3); dx2 <- pairs 1 (w1), 2 (w3); dx3 <- pairs 3 (w2), 5 (w1)
     axpy16(acc[0], s[0], w[1]); axpy16(acc[0], s[4], w[2]);
@@ -278,7 +283,7 @@ int hcm_nce_bwd(const float* bank1, const float* bank2, const float* bank3, cons
                 const float* x3, long ldx, const long long* idx, int B, int K1, int dim, float T, const float* logits,
                 const float* lse, const float* coef, float gscale, float* df, long lddf, cudaStream_t stream) {
   HCM_CHECK_ARG(dim == D, "nce: feature dim %d unsupported (128 only)", dim);
-  HCM_CHECK_ARG(bank1 && bank2 && bank3 && idx && logits && lse && coef && df, "nce_bwd: null pointer");
+  HCM_CHECK_ARG(bank1 && bank2 && bank3 && idx && logits && df && ((lse == nullptr) == (coef == nullptr)), "nce_bwd: null pointer");
   NceArgs a;
   a.bank[0] = bank1; a.bank[1] = bank2; a.bank[2] = bank3;
   a.x[0] = x1; a.x[1] = x2; a.x[2] = x3; a.ldx = ldx; a.idx = idx; a.B = B; a.K1 = K1; a.invT = 1.f / T;

@@ -454,16 +454,18 @@ long hcm_tc_conv_wpack_bytes(int B, int H, int W, int Cin, int Cout, int ks) {
   return (long)g.wbytes;
 }
 
-// Pack OIHW fp32 weights into the bf16 hi/lo slabs.  (Cin, Cout) describe the GEMM being run:
+// Pack OIHW fp32 weights into the bf16 hi/lo slabs.  `w` may point at a column block of a wider [O][ldw][ks][ks]
+// tensor (the per-branch blocks of the 1x1 projection).  (Cin, Cout) describe the GEMM being run:
 // transpose=0 -> the forward conv of w[Cout][Cin][ks][ks];  transpose=1 -> its data gradient, i.e. a conv with
 // Cin' = Cout(w), Cout' = Cin(w): pass Cin = Cout(w), Cout = Cin(w).
-int hcm_tc_conv_pack(const float* w, void* wpack, int B, int H, int W, int Cin, int Cout, int ks, int transpose,
+int hcm_tc_conv_pack(const float* w, int ldw, void* wpack, int B, int H, int W, int Cin, int Cout, int ks, int transpose,
                      cudaStream_t stream) {
   HCM_CHECK_ARG(w && wpack, "tc_conv_pack: null pointer");
   Geo g = make_geo(B, H, W, Cin, Cout, ks);
   HCM_CHECK_ARG(geo_ok(g, Cin, Cout, ks), "tc_conv_pack: unsupported geometry");
   const long total = (long)g.nslabs * g.Npad * g.KB;
-  const int wCin = transpose ? Cout : Cin;                       // inner (second) dimension of the OIHW tensor
+  // ldw: second dimension of the OIHW tensor the slice lives in (its row stride / ks^2); 0 = contiguous
+  const int wCin = ldw > 0 ? ldw : (transpose ? Cout : Cin);
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
   tc_pack_kernel<<<grid, 256, 0, stream>>>(w, reinterpret_cast<uint8_t*>(wpack), g, Cin, Cout, ks, transpose, wCin);

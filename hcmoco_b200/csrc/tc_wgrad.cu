@@ -69,7 +69,7 @@ struct WParams {
   int in_relu;
   const float* dy;
   float* dw;
-  int B, H, W, Cin, Cout, ks;
+  int B, H, W, Cin, Cout, ks, lddw;
   WGeo g;
 };
 
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(NTHREADS_W) tc_wgrad_kernel(const WParams p) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int ci = ci_lo + c0 + i;
-              if (ci < p.Cin) atomicAdd(p.dw + ((long)co * p.Cin + ci) * g.taps + tap, v[i]);
+              if (ci < p.Cin) atomicAdd(p.dw + ((long)co * p.lddw + ci) * g.taps + tap, v[i]);
             }
           }
         }
@@ -263,8 +263,9 @@ int hcm_tc_wgrad_supported(int B, int H, int W, int Cin, int Cout, int ks, int s
   return wgeo_ok(g, Cin, Cout, ks) ? 1 : 0;
 }
 
-// dw[Cout,Cin,ks,ks] += sum_pixels dy * T(x)   (stride 1; fp32 atomics across CTAs; caller zeroes dw once per step)
-int hcm_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int Cout, int ks,
+// dw[Cout,Cin,ks,ks] += sum_pixels dy * T(x)   (stride 1; fp32 atomics across CTAs; caller zeroes dw once per step).
+// lddw > 0: dw is a column block of a wider [Cout][lddw][ks][ks] tensor
+int hcm_tc_wgrad(const float* x, const float* dy, float* dw, int lddw, int B, int H, int W, int Cin, int Cout, int ks,
                  const float* in_scale, const float* in_shift, int in_relu, cudaStream_t stream) {
   HCM_CHECK_ARG(x && dy && dw, "tc_wgrad: null pointer");
   HCM_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "tc_wgrad: in_scale/in_shift must come together");
@@ -272,7 +273,7 @@ int hcm_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W
   p.g = make_wgeo(B, H, W, Cin, Cout, ks);
   HCM_CHECK_ARG(wgeo_ok(p.g, Cin, Cout, ks), "tc_wgrad: unsupported geometry (Cin=%d Cout=%d ks=%d)", Cin, Cout, ks);
   p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.in_relu = in_relu; p.dy = dy; p.dw = dw;
-  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ks = ks;
+  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ks = ks; p.lddw = lddw > 0 ? lddw : Cin;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

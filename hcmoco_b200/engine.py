@@ -86,40 +86,13 @@ class ParamStore:
     def grad(self, key):
         return self.view(self.g, key)
 
-    # ---- checkpoint layout <-> internal layout.  Only the 1x1 projection differs: its [128,Cm] matrix is
-    # stored as four per-branch column blocks, each contiguous [128,Cj] (see Engine._projection).
-    def _split_cols(self, key):
-        if key.startswith("encoder") and "_linear.weight" in key:
-            cm = self.keys[key][1]
-            for w, ch in L.WIDTHS.items():
-                if sum(ch) == cm:
-                    return ch
-        return None
-
+    # ---- every tensor is stored in exactly the checkpoint layout (OIHW convs, [out,in] linears, [2,Cin,Cout] SemGCN)
     def export(self, flat, key):
-        v = self.view(flat, key)
-        cols = self._split_cols(key)
-        if cols is None:
-            return v.reshape(self.keys[key]).clone()
-        parts, o = [], 0
-        for c in cols:
-            parts.append(v[o:o + 128 * c].reshape(128, c))
-            o += 128 * c
-        return torch.cat(parts, 1).reshape(self.keys[key]).clone()
+        return self.view(flat, key).reshape(self.keys[key]).clone()
 
     def load(self, flat, key, t):
         v = self.view(flat, key)
-        t = t.to(device=v.device, dtype=v.dtype)
-        cols = self._split_cols(key)
-        if cols is None:
-            v.copy_(t.reshape(-1))
-            return
-        t = t.reshape(128, -1)
-        o = c0 = 0
-        for c in cols:
-            v[o:o + 128 * c].copy_(t[:, c0:c0 + c].reshape(-1))
-            o += 128 * c
-            c0 += c
+        v.copy_(t.to(device=v.device, dtype=v.dtype).reshape(-1))
 
     def state_dict(self, prefix=""):
         out = OrderedDict()
@@ -167,10 +140,15 @@ class Plan:
     def on_backward(self, builder):
         self._builders.append(builder)
 
-    def finish(self):
-        for bld in reversed(self._builders):
+    def finish(self, mark=0):
+        """Run the builders in reverse registration order; returns len(bwd) after the builders >= `mark` ran."""
+        for bld in reversed(self._builders[mark:]):
+            bld()
+        n = len(self.bwd)
+        for bld in reversed(self._builders[:mark]):
             bld()
         self._builders = []
+        return n
 
     def grad(self, act):
         """Gradient buffer of a materialised act + whether the next writer must accumulate."""
@@ -197,7 +175,8 @@ class Plan:
 
 class Engine:
     def __init__(self, K, width=18, stage=1, skeleton="mpii", B=2, R=224, n_data=20000, nce_k=16384, nce_t=0.07,
-                 nce_m=0.5, temperature=0.07, num_samples=400, feat_dim=128, world_size=1, train=True, use_tc=True):
+                 nce_m=0.5, temperature=0.07, num_samples=400, feat_dim=128, world_size=1, train=True, use_tc=True,
+                 store=None):
         assert feat_dim == 128, "the NCE / loss kernels are specialised for feat_dim=128"
         assert R % 32 == 0, "HRNet needs the input side to be a multiple of 32"
         assert B >= 2, "the reference collapses B=1 (mem_bank.py:39 out.squeeze())"
@@ -211,7 +190,8 @@ class Engine:
         self.use_tc = use_tc     # tensor-core path for the stride-1 convs (SIMT fp32 implicit GEMM otherwise)
         self.ch = L.WIDTHS[width]
         self.cm = sum(self.ch)
-        self.store = ParamStore(K, L.model_keys(width, stage, skeleton, feat_dim))
+        # `store`: parameter storage shared with an api.HCMoCoModel (several engines = several batch shapes, one model)
+        self.store = store if store is not None else ParamStore(K, L.model_keys(width, stage, skeleton, feat_dim))
         self.edge_rows = torch.tensor(rows, dtype=torch.int32, device=K.device)
         self.edge_cols = torch.tensor(cols, dtype=torch.int32, device=K.device)
         self.banks = None
@@ -264,10 +244,11 @@ class Engine:
         # losses (the builders registered here run first in the backward)
         self.losses = K.zeros(16)     # 0-5 nce, 6-7 dense, 8-9 joint, 10 scl
         self.accs = K.zeros(16)       # 0-5 nce, 6-7 dense, 8-9 joint
+        n_model_builders = len(p._builders)
         self._nce()
         if self.stage == 2:
             self._stage2_losses()
-        p.finish()
+        self.n_loss_bwd = p.finish(n_model_builders)      # bwd[:n_loss_bwd] = loss kernels, the rest = model backward
         self.built = True
         return self
 
@@ -290,7 +271,7 @@ class Engine:
             nb = K.tc_conv_wpack_bytes(B, H, W, cin, cout, ks)
             wp_f = K.empty((nb + 3) // 4)
             rows = K.colstat_rows(P, cout)
-            p.f(K.tc_conv_pack, w, wp_f, B, H, W, cin, cout, ks, 0)
+            p.f(K.tc_conv_pack, w, 0, wp_f, B, H, W, cin, cout, ks, 0)
             p.f(K.tc_conv, x.data, wp_f, None, y, B, H, W, cin, cout, ks, x.scale, x.shift, int(x.relu), 0)
             p.f(K.bn_stats, y, P, cout, self.part)
         else:
@@ -318,7 +299,7 @@ class Engine:
                 spec["g_out"], spec["g_acc"], P, cout)
             dy = spec["dy"]
             if self.use_tc and K.tc_wgrad_supported(B, H, W, cin, cout, ks, stride):
-                p.b(K.tc_wgrad, x.data, dy, st.grad(ck + ".weight"), B, H, W, cin, cout, ks, x.scale, x.shift, int(x.relu))
+                p.b(K.tc_wgrad, x.data, dy, st.grad(ck + ".weight"), 0, B, H, W, cin, cout, ks, x.scale, x.shift, int(x.relu))
             else:
                 p.b(K.conv2d_wgrad, x.data, dy, st.grad(ck + ".weight"), B, H, W, cin, cout, ks, stride, x.scale, x.shift,
                     int(x.relu))
@@ -333,7 +314,7 @@ class Engine:
                     # data gradient = the same tensor-core conv run on dy with transposed + flipped weights
                     nbt = K.tc_conv_wpack_bytes(B, H, W, cout, cin, ks)
                     wp_t = K.empty((nbt + 3) // 4)
-                    p.b(K.tc_conv_pack, w, wp_t, B, H, W, cout, cin, ks, 1)
+                    p.b(K.tc_conv_pack, w, 0, wp_t, B, H, W, cout, cin, ks, 1)
                     p.b(K.tc_conv, dy, wp_t, None, gx, B, H, W, cout, cin, ks, None, None, 0, acc)
                 else:
                     p.b(K.conv2d_dgrad, dy, w, gx, B, H, W, cin, cout, ks, stride, acc)
@@ -621,22 +602,22 @@ class Engine:
     # summed by fuse_sum: the [B,Cm,h,h] merged map is never materialised.
     def _projection(self, key, feats):
         K, p, st, B, h = self.K, self.plan, self.store, self.B, self.h
-        wflat, bias = st.param(key + ".weight"), st.param(key + ".bias")
-        gflat = st.grad(key + ".weight")
+        wfull, bias = st.param(key + ".weight"), st.param(key + ".bias")
+        gfull = st.grad(key + ".weight")
+        cm = self.cm
         ws, gs, ys, o = [], [], [], 0
         for j, ft in enumerate(feats):
-            n = 128 * ft.C
-            ws.append(wflat[o:o + n])
-            gs.append(gflat[o:o + n])
-            o += n
+            # column block j of the [128, Cm] matrix: element (n, c) at n*Cm + o + c  (row stride ldw = Cm)
+            ws.append(wfull[o:])
+            gs.append(gfull[o:])
+            o += ft.C
             ft.consumers += 1
             y = K.empty(B, ft.H, ft.W, 128)
-            if self.use_tc and K.tc_conv_supported(B, ft.H, ft.W, ft.C, 128, 1, 1):
-                wp = K.empty((K.tc_conv_wpack_bytes(B, ft.H, ft.W, ft.C, 128, 1) + 3) // 4)
-                p.f(K.tc_conv_pack, ws[j], wp, B, ft.H, ft.W, ft.C, 128, 1, 0)
-                p.f(K.tc_conv, ft.data, wp, None, y, B, ft.H, ft.W, ft.C, 128, 1, None, None, 0, 0)
-            else:
-                p.f(K.conv2d_fwd, ft.data, ws[j], None, y, B, ft.H, ft.W, ft.C, 128, 1, 1, None, None, 0, None)
+            if not (self.use_tc and K.tc_conv_supported(B, ft.H, ft.W, ft.C, 128, 1, 1)):
+                raise NotImplementedError("the 1x1 projection runs on the tensor-core path only")
+            wp = K.empty((K.tc_conv_wpack_bytes(B, ft.H, ft.W, ft.C, 128, 1) + 3) // 4)
+            p.f(K.tc_conv_pack, ws[j], cm, wp, B, ft.H, ft.W, ft.C, 128, 1, 0)
+            p.f(K.tc_conv, ft.data, wp, None, y, B, ft.H, ft.W, ft.C, 128, 1, None, None, 0, 0)
             ys.append(y)
         out = Act(K.empty(B, h, h, 128), B, h, h, 128)
         log2f = torch.tensor([0, 1, 2, 3], dtype=torch.int32)
@@ -655,17 +636,11 @@ class Engine:
                 else:
                     Gj = K.empty(B, ft.H, ft.W, 128)
                     p.b(K.upsample_adjoint, G, Gj, 0, B, h, h, 128, j)
-                if self.use_tc and K.tc_wgrad_supported(B, ft.H, ft.W, ft.C, 128, 1, 1):
-                    p.b(K.tc_wgrad, ft.data, Gj, gs[j], B, ft.H, ft.W, ft.C, 128, 1, None, None, 0)
-                else:
-                    p.b(K.conv2d_wgrad, ft.data, Gj, gs[j], B, ft.H, ft.W, ft.C, 128, 1, 1, None, None, 0)
+                p.b(K.tc_wgrad, ft.data, Gj, gs[j], cm, B, ft.H, ft.W, ft.C, 128, 1, None, None, 0)
                 gx, acc = p.grad(ft)
-                if self.use_tc and K.tc_conv_supported(B, ft.H, ft.W, 128, ft.C, 1, 1):
-                    wpt = K.empty((K.tc_conv_wpack_bytes(B, ft.H, ft.W, 128, ft.C, 1) + 3) // 4)
-                    p.b(K.tc_conv_pack, ws[j], wpt, B, ft.H, ft.W, 128, ft.C, 1, 1)
-                    p.b(K.tc_conv, Gj, wpt, None, gx, B, ft.H, ft.W, 128, ft.C, 1, None, None, 0, acc)
-                else:
-                    p.b(K.conv2d_dgrad, Gj, ws[j], gx, B, ft.H, ft.W, ft.C, 128, 1, 1, acc)
+                wpt = K.empty((K.tc_conv_wpack_bytes(B, ft.H, ft.W, 128, ft.C, 1) + 3) // 4)
+                p.b(K.tc_conv_pack, ws[j], cm, wpt, B, ft.H, ft.W, 128, ft.C, 1, 1)
+                p.b(K.tc_conv, Gj, wpt, None, gx, B, ft.H, ft.W, 128, ft.C, 1, None, None, 0, acc)
 
         p.on_backward(backward)
         return out
@@ -798,6 +773,44 @@ class Engine:
     def backward(self):
         self.K.zero(self.store.g, self.store.n * self.store.g.element_size())
         Plan.run(self.plan.bwd)
+
+    # ---- model-only programs for the autograd bridge (api.HCMoCoModel): the caller owns the losses
+    def forward_model(self):
+        Plan.run(self.plan.fwd[:self.n_model_fwd])
+
+    def seed_output_grads(self, gf, g_feat3=None, g_lm1=None, g_lm2=None):
+        """Write d(loss)/d(outputs) into the buffers the model-backward program starts from."""
+        B, J, h = self.B, self.J, self.h
+        self.df.copy_(gf) if gf is not None else self.df.zero_()
+        slot = self.feat3_slot
+        if slot["grad"] is None:
+            slot["grad"] = self.K.empty(B, J, 128)
+        if g_feat3 is not None:
+            slot["grad"].copy_(g_feat3)
+        else:
+            slot["grad"].zero_()
+        if self.stage == 2:
+            for act, g in ((self.lm1, g_lm1), (self.lm2, g_lm2)):
+                if g is not None:
+                    act.grad.copy_(g.permute(0, 2, 3, 1))
+                else:
+                    act.grad.zero_()
+
+    def backward_model(self):
+        self.K.zero(self.store.g, self.store.n * self.store.g.element_size())
+        Plan.run(self.plan.bwd[self.n_loss_bwd:])
+
+    def draw_dense(self, injected=None):
+        """Dense pixel samples: S draws with replacement from each sample's nearest-resized depth mask
+        (contrast_trainer.py:674-685); rows of samples the mask drops are ignored downstream."""
+        if injected is not None:
+            self.dense_idx.copy_(injected)
+            return
+        step = self.R // self.h
+        m = self.depth_mask[:, ::step, ::step][:, :self.h, :self.h].reshape(self.B, -1)
+        has = m.sum(1, keepdim=True) > 0
+        w = torch.where(has, (m != 0).to(m.dtype), torch.ones_like(m))
+        self.dense_idx.copy_(torch.multinomial(w, self.S, replacement=True))
 
     def update_banks(self, all_f=None, all_index=None):
         """mem_bank.py:195-203 with the all-gathered embeddings (contrast_trainer.py:578-579)."""

@@ -51,8 +51,9 @@ int hcm_gemm(const float* A, const float* Bm, const float* bias, float* C, int b
 int hcm_tc_conv_supported(int B, int H, int W, int Cin, int Cout, int ks, int stride);
 long hcm_tc_conv_wpack_bytes(int B, int H, int W, int Cin, int Cout, int ks);
 /* transpose=0: pack w[Cout][Cin][ks][ks] for the forward conv; transpose=1: pack the same tensor for its data
- * gradient seen as a conv with Cin' = Cout(w), Cout' = Cin(w) (pass those as Cin, Cout) */
-int hcm_tc_conv_pack(const float* w, void* wpack, int B, int H, int W, int Cin, int Cout, int ks, int transpose,
+ * gradient seen as a conv with Cin' = Cout(w), Cout' = Cin(w) (pass those as Cin, Cout).  ldw > 0: `w` is a column block
+ * of a wider [O][ldw][ks][ks] tensor (per-branch blocks of the 1x1 projection); lddw likewise for hcm_tc_wgrad */
+int hcm_tc_conv_pack(const float* w, int ldw, void* wpack, int B, int H, int W, int Cin, int Cout, int ks, int transpose,
                      cudaStream_t stream);
 /* y[B,H,W,Cout] (+)= conv(T(x[B,H,W,Cin])) (+bias), stride 1, pad (ks-1)/2 */
 int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, int B, int H, int W, int Cin, int Cout,
@@ -60,7 +61,7 @@ int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, 
 
 /* tensor-core weight gradient (tc_wgrad.cu): dw[Cout,Cin,ks,ks] += sum_pixels dy * T(x), stride 1 */
 int hcm_tc_wgrad_supported(int B, int H, int W, int Cin, int Cout, int ks, int stride);
-int hcm_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int Cout, int ks,
+int hcm_tc_wgrad(const float* x, const float* dy, float* dw, int lddw, int B, int H, int W, int Cin, int Cout, int ks,
                  const float* in_scale, const float* in_shift, int in_relu, cudaStream_t stream);
 
 /* ---- train-mode batch norm (bn.cu) : nn.BatchNorm2d(momentum=0.01) official_hrnet.py:22-23 (+ReLU /
@@ -106,6 +107,7 @@ int hcm_nce_logits(const float* bank1, const float* bank2, const float* bank3, c
                    cudaStream_t stream);
 int hcm_nce_loss(const float* logits, int B, int K1, const long long* use_depth, const long long* use_rgb, float* lse,
                  float* l0, float* hit, float* coef, float* loss6, float* acc6, cudaStream_t stream);
+/* lse == coef == NULL: `logits` holds d(loss)/d(logits) (backward of the logits-returning CMCMem3.forward) */
 int hcm_nce_bwd(const float* bank1, const float* bank2, const float* bank3, const float* x1, const float* x2,
                 const float* x3, long ldx, const long long* idx, int B, int K1, int dim, float T, const float* logits,
                 const float* lse, const float* coef, float gscale, float* df, long lddf, cudaStream_t stream);

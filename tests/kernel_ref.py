@@ -107,13 +107,15 @@ class TorchKernels:
     def tc_conv_wpack_bytes(self, B, H, W, Cin, Cout, ks):
         return Cin * Cout * ks * ks * 8          # room for fp64 in the exact-wiring tests
 
-    def tc_conv_pack(self, w, wpack, B, H, W, Cin, Cout, ks, transpose):
+    def tc_conv_pack(self, w, ldw, wpack, B, H, W, Cin, Cout, ks, transpose):
         # the "packed" form of the reference is simply the effective OIHW weight of the GEMM being run
-        wv = w.reshape(-1)[:Cin * Cout * ks * ks]
+        O, I = (Cin, Cout) if transpose else (Cout, Cin)                         # dims of the OIHW slice
+        ld = ldw if ldw > 0 else I
+        wv = torch.as_strided(w, (O, I, ks, ks), (ld * ks * ks, ks * ks, ks, 1), w.storage_offset())
         if transpose:
-            weff = wv.reshape(Cin, Cout, ks, ks).transpose(0, 1).flip(2, 3)     # w is [Cout(w)=Cin'][Cin(w)=Cout']
+            weff = wv.transpose(0, 1).flip(2, 3)                                 # w is [Cout(w)=Cin'][Cin(w)=Cout']
         else:
-            weff = wv.reshape(Cout, Cin, ks, ks)
+            weff = wv
         wpack.reshape(-1).view(w.dtype)[:weff.numel()].copy_(weff.reshape(-1))
         return 0
 
@@ -130,8 +132,12 @@ class TorchKernels:
     def tc_wgrad_supported(self, B, H, W, Cin, Cout, ks, stride):
         return self.tc_conv_supported(B, H, W, Cin, Cout, ks, stride)
 
-    def tc_wgrad(self, x, dy, dw, B, H, W, Cin, Cout, ks, sc, sh, relu):
-        return self.conv2d_wgrad(x, dy, dw, B, H, W, Cin, Cout, ks, 1, sc, sh, relu)
+    def tc_wgrad(self, x, dy, dw, lddw, B, H, W, Cin, Cout, ks, sc, sh, relu):
+        ld = lddw if lddw > 0 else Cin
+        tmp = torch.zeros(Cout, Cin, ks, ks, dtype=dw.dtype, device=dw.device)
+        self.conv2d_wgrad(x, dy, tmp, B, H, W, Cin, Cout, ks, 1, sc, sh, relu)
+        torch.as_strided(dw, (Cout, Cin, ks, ks), (ld * ks * ks, ks * ks, ks, 1), dw.storage_offset()).add_(tmp)
+        return 0
 
     def gemm(self, A, Bm, bias, C, batch, M, N, K, sAm, sAk, sBk, sBn, sCm, bsA, bsB, bsC, alpha, accumulate):
         a = torch.as_strided(A.reshape(-1), (batch, M, K), (bsA, sAm, sAk))
@@ -265,9 +271,10 @@ class TorchKernels:
 
     def upsample_adjoint(self, g, out, accumulate, B, H, W, C, log2f):
         f = 1 << log2f
-        src = torch.zeros(B, C, H // f, W // f, device=g.device, dtype=g.dtype, requires_grad=True)
-        up = _up(src, f)
-        (gr,) = torch.autograd.grad(up, src, _nchw(g, B, H, W, C))
+        with torch.enable_grad():          # may be called from inside an autograd.Function.backward (grad mode off)
+            src = torch.zeros(B, C, H // f, W // f, device=g.device, dtype=g.dtype, requires_grad=True)
+            up = _up(src, f)
+            (gr,) = torch.autograd.grad(up, src, _nchw(g, B, H, W, C).detach())
         r = _nhwc(gr).reshape(-1)
         if accumulate:
             out.reshape(-1).add_(r)
@@ -325,9 +332,12 @@ class TorchKernels:
         L = logits.reshape(6, B, K1)
         dfv = torch.as_strided(df, (B, 3, dim), (lddf, dim, 1), df.storage_offset())
         for q, (p, bq) in enumerate(self.PAIRS):
-            s = torch.exp(L[q] - lse.reshape(6, B)[q].unsqueeze(1))
-            s[:, 0] -= 1.0
-            s = s * (coef.reshape(6, B)[q] * gscale / T).unsqueeze(1)
+            if lse is None:          # generic: `logits` holds d(loss)/d(logits)
+                s = L[q] * (gscale / T)
+            else:
+                s = torch.exp(L[q] - lse.reshape(6, B)[q].unsqueeze(1))
+                s[:, 0] -= 1.0
+                s = s * (coef.reshape(6, B)[q] * gscale / T).unsqueeze(1)
             dfv[:, p] += torch.bmm(s.unsqueeze(1), w[bq]).squeeze(1)
         return 0
 

@@ -331,7 +331,7 @@ def test_tc_conv(KK, shape):
     sc, sh = rnd(Cin, seed=1).abs() + 0.5, rnd(Cin, seed=2)
     bias = rnd(Cout, seed=5)
     wp = torch.zeros((kc.tc_conv_wpack_bytes(B, H, W, Cin, Cout, ks) + 3) // 4, device=DEV)
-    kc.tc_conv_pack(w, wp, B, H, W, Cin, Cout, ks, 0)
+    kc.tc_conv_pack(w, 0, wp, B, H, W, Cin, Cout, ks, 0)
     y1, y2 = rnd(B, H, W, Cout, seed=7), rnd(B, H, W, Cout, seed=7)
     # forward, BN+ReLU applied on load
     kc.tc_conv(x, wp, None, y1, B, H, W, Cin, Cout, ks, sc, sh, 1, 0)
@@ -346,7 +346,7 @@ def test_tc_conv(KK, shape):
     if kc.tc_conv_supported(B, H, W, Cout, Cin, ks, 1):
         dy = rnd(B, H, W, Cout, seed=9)
         wpt = torch.zeros((kc.tc_conv_wpack_bytes(B, H, W, Cout, Cin, ks) + 3) // 4, device=DEV)
-        kc.tc_conv_pack(w, wpt, B, H, W, Cout, Cin, ks, 1)
+        kc.tc_conv_pack(w, 0, wpt, B, H, W, Cout, Cin, ks, 1)
         dx1, dx2 = torch.zeros(B, H, W, Cin, device=DEV), torch.zeros(B, H, W, Cin, device=DEV)
         kc.tc_conv(dy, wpt, None, dx1, B, H, W, Cout, Cin, ks, None, None, 0, 0)
         kr.conv2d_dgrad(dy, w, dx2, B, H, W, Cin, Cout, ks, 1, 0)
@@ -363,9 +363,9 @@ def test_tc_wgrad(KK, shape):
     sc, sh = rnd(Cin, seed=1).abs() + 0.5, rnd(Cin, seed=2)
     dw1 = rnd(Cout, Cin, ks, ks, seed=6)
     dw2 = dw1.clone()
-    kc.tc_wgrad(x, dy, dw1, B, H, W, Cin, Cout, ks, sc, sh, 1)
+    kc.tc_wgrad(x, dy, dw1, 0, B, H, W, Cin, Cout, ks, sc, sh, 1)
     kr.conv2d_wgrad(x, dy, dw2, B, H, W, Cin, Cout, ks, 1, sc, sh, 1)
     assert rel(dw1, dw2) < 3e-5, rel(dw1, dw2)
-    kc.tc_wgrad(x, dy, dw1, B, H, W, Cin, Cout, ks, None, None, 0)
+    kc.tc_wgrad(x, dy, dw1, 0, B, H, W, Cin, Cout, ks, None, None, 0)
     kr.conv2d_wgrad(x, dy, dw2, B, H, W, Cin, Cout, ks, 1, None, None, 0)
     assert rel(dw1, dw2) < 3e-5, rel(dw1, dw2)

@@ -120,3 +120,50 @@ def test_cuda_graph_replay_is_identical(K):
         ra, rb = a.results(), b.results()
         assert rel(rb["loss"], ra["loss"]) < 1e-5      # atomics (wgrad split-K, scatter) reorder fp32 sums
     assert rel(b.store.p, a.store.p) < 1e-3
+
+
+def test_reference_surface_on_gpu(K, tmp_path):
+    """build_model / build_mem / build_contrast on the GPU: the trainer's fused, CUDA-graph-replayed step against the
+    oracle (loss and embeddings within 1e-3), the autograd path (model(...) + loss.backward()) against the fused path,
+    and a checkpoint round trip."""
+    from oracle import hcmoco_oracle as O
+    from hcmoco_b200 import api
+    from test_api_cpu import make_opt
+    cfg = CASES["s3_stage2_w18_b3_r64_coco"]
+    layout, P, mom, banks = oracle_state(cfg, torch.float32)
+    opt = make_opt(cfg, cuda_graph=True, model_folder=str(tmp_path), tb_folder=str(tmp_path))
+    model, _ = api.build_model(opt)
+    assert isinstance(model.K, type(K)) and next(model.parameters()).is_cuda
+    model.store.load_state_dict(P)
+    mem = api.build_mem(opt, cfg["n"])
+    for i in range(3):
+        getattr(mem, "memory_%d" % (i + 1)).copy_(banks[i])
+    trainer = api.build_contrast(opt)
+    _, _, optimizer = trainer.wrap_up(model, None, torch.optim.SGD(model.parameters(), lr=0.03, momentum=0.9, weight_decay=1e-4))
+    batch, nce, dense = make_inputs(cfg, 0)
+    # autograd path first (does not touch BN running stats of the comparison below: reload state after)
+    dev = {k: v.cuda() for k, v in batch.items()}
+    _, _, feat3, f, aux = model(dev["x"], dev["skeleton"], return_fm=True)
+    (f.square().sum() + aux["linear_merge1"].square().mean() + feat3.mean()).backward()
+    g_auto = model.encoder1.conv1.weight.grad.clone()
+    assert torch.isfinite(g_auto).all() and float(g_auto.abs().sum()) > 0
+    model.store.load_state_dict(P)
+    ref = O.train_step(P, mom, banks, batch, nce, dense, width=cfg["width"], skeleton=cfg["skeleton"], stage=cfg["stage"],
+                       first=True)
+    data = [batch["x"], batch["index"], batch["skeleton"], None, batch["joints_yx"], batch["joints_vis"], batch["use_depth"],
+            batch["depth_mask"], None]
+    mem.injected_idx = nce.cuda()
+    trainer.injected_dense_idx = dense.cuda()
+    res = trainer.train_step(model, mem, optimizer, data)()
+    eng = model.engine_for(cfg["B"], cfg["R"])
+    assert hasattr(eng, "graph")
+    assert rel(res["loss"], ref["loss"]) < 1e-3 and rel(eng.f, ref["f"]) < 1e-3
+    assert rel(res["dense_losses"], torch.stack(ref["dense_losses"])) < 1e-3
+    for i in range(3):
+        assert rel(getattr(mem, "memory_%d" % (i + 1)), banks[i]) < 1e-4
+    trainer.save(model, None, mem, optimizer, epoch=3)
+    ck = torch.load(os.path.join(str(tmp_path), "current.pth"), map_location="cpu", weights_only=False)
+    assert list(ck["model"])[0] == "module.encoder1.conv1.weight" and ck["epoch"] == 3
+    model2, _ = api.build_model(make_opt(cfg))
+    model2.store.load_state_dict(ck["model"])
+    assert torch.equal(model2.store.p, model.store.p)
