@@ -132,13 +132,14 @@ class HCMoCoModel(nn.Module):
                          int(getattr(o, "nce_k", 16384)), float(getattr(o, "nce_t", 0.07)), float(getattr(o, "nce_m", 0.5)),
                          float(getattr(o, "temperature", 0.07)), int(getattr(o, "pri3d_num_samples_per_image", 400)),
                          store=self.store)
-            if mem is not None:
-                eng.banks = [mem.memory_1, mem.memory_2, mem.memory_3]
-            else:
-                eng.init_banks()
+            if mem is None:
+                eng.init_banks()          # placeholder rows; only the model programs run without a memory
             eng.build()
             self._engines[key] = eng
-        return self._engines[key]
+        eng = self._engines[key]
+        if mem is not None:
+            eng.banks = [mem.memory_1, mem.memory_2, mem.memory_3]
+        return eng
 
     def attach_memory(self, mem):
         self._mem = mem
