@@ -272,7 +272,7 @@ class Engine:
             wp_f = K.empty((nb + 3) // 4)
             rows = K.colstat_rows(P, cout)
             p.f(K.tc_conv_pack, w, 0, wp_f, B, H, W, cin, cout, ks, 0)
-            p.f(K.tc_conv, x.data, wp_f, None, y, B, H, W, cin, cout, ks, x.scale, x.shift, int(x.relu), 0)
+            p.f(K.tc_conv, x.data, wp_f, None, y, B, H, W, cin, cout, ks, stride, x.scale, x.shift, int(x.relu), 0)
             p.f(K.bn_stats, y, P, cout, self.part)
         else:
             rows = K.conv2d_stat_rows(B, H, W, cin, cout, ks, stride)
@@ -310,12 +310,12 @@ class Engine:
                     gx, acc = x.grad, 0
                 else:
                     gx, acc = p.grad(x)
-                if tc and K.tc_conv_supported(B, H, W, cout, cin, ks, stride):
+                if tc and stride == 1 and K.tc_conv_supported(B, H, W, cout, cin, ks, 1):
                     # data gradient = the same tensor-core conv run on dy with transposed + flipped weights
                     nbt = K.tc_conv_wpack_bytes(B, H, W, cout, cin, ks)
                     wp_t = K.empty((nbt + 3) // 4)
                     p.b(K.tc_conv_pack, w, 0, wp_t, B, H, W, cout, cin, ks, 1)
-                    p.b(K.tc_conv, dy, wp_t, None, gx, B, H, W, cout, cin, ks, None, None, 0, acc)
+                    p.b(K.tc_conv, dy, wp_t, None, gx, B, H, W, cout, cin, ks, 1, None, None, 0, acc)
                 else:
                     p.b(K.conv2d_dgrad, dy, w, gx, B, H, W, cin, cout, ks, stride, acc)
 
@@ -617,7 +617,7 @@ class Engine:
                 raise NotImplementedError("the 1x1 projection runs on the tensor-core path only")
             wp = K.empty((K.tc_conv_wpack_bytes(B, ft.H, ft.W, ft.C, 128, 1) + 3) // 4)
             p.f(K.tc_conv_pack, ws[j], cm, wp, B, ft.H, ft.W, ft.C, 128, 1, 0)
-            p.f(K.tc_conv, ft.data, wp, None, y, B, ft.H, ft.W, ft.C, 128, 1, None, None, 0, 0)
+            p.f(K.tc_conv, ft.data, wp, None, y, B, ft.H, ft.W, ft.C, 128, 1, 1, None, None, 0, 0)
             ys.append(y)
         out = Act(K.empty(B, h, h, 128), B, h, h, 128)
         log2f = torch.tensor([0, 1, 2, 3], dtype=torch.int32)
@@ -640,7 +640,7 @@ class Engine:
                 gx, acc = p.grad(ft)
                 wpt = K.empty((K.tc_conv_wpack_bytes(B, ft.H, ft.W, 128, ft.C, 1) + 3) // 4)
                 p.b(K.tc_conv_pack, ws[j], cm, wpt, B, ft.H, ft.W, 128, ft.C, 1, 1)
-                p.b(K.tc_conv, Gj, wpt, None, gx, B, ft.H, ft.W, 128, ft.C, 1, None, None, 0, acc)
+                p.b(K.tc_conv, Gj, wpt, None, gx, B, ft.H, ft.W, 128, ft.C, 1, 1, None, None, 0, acc)
 
         p.on_backward(backward)
         return out

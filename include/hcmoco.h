@@ -55,9 +55,10 @@ long hcm_tc_conv_wpack_bytes(int B, int H, int W, int Cin, int Cout, int ks);
  * of a wider [O][ldw][ks][ks] tensor (per-branch blocks of the 1x1 projection); lddw likewise for hcm_tc_wgrad */
 int hcm_tc_conv_pack(const float* w, int ldw, void* wpack, int B, int H, int W, int Cin, int Cout, int ks, int transpose,
                      cudaStream_t stream);
-/* y[B,H,W,Cout] (+)= conv(T(x[B,H,W,Cin])) (+bias), stride 1, pad (ks-1)/2 */
+/* y[B,Ho,Wo,Cout] (+)= conv(T(x[B,H,W,Cin])) (+bias), 3x3 stride 1|2 or 1x1, pad (ks-1)/2 */
 int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, int B, int H, int W, int Cin, int Cout,
-                int ks, const float* in_scale, const float* in_shift, int in_relu, int accumulate, cudaStream_t stream);
+                int ks, int stride, const float* in_scale, const float* in_shift, int in_relu, int accumulate,
+                cudaStream_t stream);
 
 /* tensor-core weight gradient (tc_wgrad.cu): dw[Cout,Cin,ks,ks] += sum_pixels dy * T(x), stride 1 */
 int hcm_tc_wgrad_supported(int B, int H, int W, int Cin, int Cout, int ks, int stride);

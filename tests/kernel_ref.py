@@ -102,7 +102,8 @@ class TorchKernels:
 
     # ---------------------------------------------------------------- tc_conv.cu (exact fp32 statement)
     def tc_conv_supported(self, B, H, W, Cin, Cout, ks, stride):
-        return int(stride == 1 and ks in (1, 3) and Cin % 2 == 0 and Cout % 2 == 0 and Cin <= 256 and Cout <= 256)
+        ok = (ks == 3 and stride in (1, 2)) or (ks == 1 and stride == 1)
+        return int(ok and Cin % 2 == 0 and Cout % 2 == 0 and Cin <= 256 and Cout <= 256 and (stride == 1 or (H % 2 == 0 and W % 2 == 0)))
 
     def tc_conv_wpack_bytes(self, B, H, W, Cin, Cout, ks):
         return Cin * Cout * ks * ks * 8          # room for fp64 in the exact-wiring tests
@@ -119,10 +120,10 @@ class TorchKernels:
         wpack.reshape(-1).view(w.dtype)[:weff.numel()].copy_(weff.reshape(-1))
         return 0
 
-    def tc_conv(self, x, wpack, bias, y, B, H, W, Cin, Cout, ks, sc, sh, relu, accumulate):
+    def tc_conv(self, x, wpack, bias, y, B, H, W, Cin, Cout, ks, stride, sc, sh, relu, accumulate):
         weff = wpack.reshape(-1).view(x.dtype)[:Cin * Cout * ks * ks].reshape(Cout, Cin, ks, ks)
         xin = _tf(x, sc, sh, relu, Cin).reshape(B, H, W, Cin).permute(0, 3, 1, 2)
-        o = _nhwc(F.conv2d(xin, weff, bias, 1, (ks - 1) // 2)).reshape(-1)
+        o = _nhwc(F.conv2d(xin, weff, bias, stride, (ks - 1) // 2)).reshape(-1)
         if accumulate:
             y.reshape(-1).add_(o)
         else:
@@ -130,7 +131,7 @@ class TorchKernels:
         return 0
 
     def tc_wgrad_supported(self, B, H, W, Cin, Cout, ks, stride):
-        return self.tc_conv_supported(B, H, W, Cin, Cout, ks, stride)
+        return int(stride == 1 and self.tc_conv_supported(B, H, W, Cin, Cout, ks, stride))
 
     def tc_wgrad(self, x, dy, dw, lddw, B, H, W, Cin, Cout, ks, sc, sh, relu):
         ld = lddw if lddw > 0 else Cin

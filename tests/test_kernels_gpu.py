@@ -334,11 +334,11 @@ def test_tc_conv(KK, shape):
     kc.tc_conv_pack(w, 0, wp, B, H, W, Cin, Cout, ks, 0)
     y1, y2 = rnd(B, H, W, Cout, seed=7), rnd(B, H, W, Cout, seed=7)
     # forward, BN+ReLU applied on load
-    kc.tc_conv(x, wp, None, y1, B, H, W, Cin, Cout, ks, sc, sh, 1, 0)
+    kc.tc_conv(x, wp, None, y1, B, H, W, Cin, Cout, ks, 1, sc, sh, 1, 0)
     kr.conv2d_fwd(x, w, None, y2, B, H, W, Cin, Cout, ks, 1, sc, sh, 1, None)
     assert rel(y1, y2) < 3e-5, rel(y1, y2)
     # plain + bias + accumulate
-    kc.tc_conv(x, wp, bias, y1, B, H, W, Cin, Cout, ks, None, None, 0, 1)
+    kc.tc_conv(x, wp, bias, y1, B, H, W, Cin, Cout, ks, 1, None, None, 0, 1)
     y3 = torch.zeros_like(y2)
     kr.conv2d_fwd(x, w, bias, y3, B, H, W, Cin, Cout, ks, 1, None, None, 0, None)
     assert rel(y1, y2 + y3) < 3e-5
@@ -348,7 +348,7 @@ def test_tc_conv(KK, shape):
         wpt = torch.zeros((kc.tc_conv_wpack_bytes(B, H, W, Cout, Cin, ks) + 3) // 4, device=DEV)
         kc.tc_conv_pack(w, 0, wpt, B, H, W, Cout, Cin, ks, 1)
         dx1, dx2 = torch.zeros(B, H, W, Cin, device=DEV), torch.zeros(B, H, W, Cin, device=DEV)
-        kc.tc_conv(dy, wpt, None, dx1, B, H, W, Cout, Cin, ks, None, None, 0, 0)
+        kc.tc_conv(dy, wpt, None, dx1, B, H, W, Cout, Cin, ks, 1, None, None, 0, 0)
         kr.conv2d_dgrad(dy, w, dx2, B, H, W, Cin, Cout, ks, 1, 0)
         assert rel(dx1, dx2) < 3e-5, rel(dx1, dx2)
 
@@ -369,3 +369,26 @@ def test_tc_wgrad(KK, shape):
     kc.tc_wgrad(x, dy, dw1, 0, B, H, W, Cin, Cout, ks, None, None, 0)
     kr.conv2d_wgrad(x, dy, dw2, B, H, W, Cin, Cout, ks, 1, None, None, 0)
     assert rel(dw1, dw2) < 3e-5, rel(dw1, dw2)
+
+
+TC_S2 = [(2, 32, 32, 18, 18), (2, 16, 16, 18, 36), (3, 8, 8, 36, 72), (2, 64, 64, 64, 64), (2, 16, 16, 72, 144), (2, 8, 8, 18, 144),
+         (4, 64, 64, 18, 18), (2, 32, 32, 32, 64)]
+
+
+@pytest.mark.parametrize("shape", TC_S2)
+def test_tc_conv_stride2(KK, shape):
+    """3x3 stride-2 convolution on tensor cores: the halo is staged space-to-depth (4 parity planes)."""
+    B, H, W, Cin, Cout = shape
+    kc, kr = KK
+    assert kc.tc_conv_supported(B, H, W, Cin, Cout, 3, 2)
+    x, w = rnd(B, H, W, Cin), rnd(Cout, Cin, 3, 3, scale=0.1)
+    sc, sh = rnd(Cin, seed=1).abs() + 0.5, rnd(Cin, seed=2)
+    wp = torch.zeros((kc.tc_conv_wpack_bytes(B, H, W, Cin, Cout, 3) + 3) // 4, device=DEV)
+    kc.tc_conv_pack(w, 0, wp, B, H, W, Cin, Cout, 3, 0)
+    y1, y2 = rnd(B, H // 2, W // 2, Cout, seed=7), rnd(B, H // 2, W // 2, Cout, seed=7)
+    kc.tc_conv(x, wp, None, y1, B, H, W, Cin, Cout, 3, 2, sc, sh, 1, 0)
+    kr.conv2d_fwd(x, w, None, y2, B, H, W, Cin, Cout, 3, 2, sc, sh, 1, None)
+    assert rel(y1, y2) < 3e-5, rel(y1, y2)
+    kc.tc_conv(x, wp, None, y1, B, H, W, Cin, Cout, 3, 2, None, None, 0, 0)
+    kr.conv2d_fwd(x, w, None, y2, B, H, W, Cin, Cout, 3, 2, None, None, 0, None)
+    assert rel(y1, y2) < 3e-5, rel(y1, y2)
