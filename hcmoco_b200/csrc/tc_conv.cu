@@ -32,6 +32,7 @@ constexpr int MAXG = 8;
 constexpr int MAX_LPAD = 512;
 constexpr int HDR_BYTES = 4096 + 2 * MAX_LPAD * 4 * 4 + 1024;   // barriers/tmem ptr/scale/shift | 2 src tables [Lpad][4] | unit table
 constexpr int MAX_UNITS = 256;
+constexpr int MAX_STEPS = 144;                // 9 taps x 256/16 channels
 
 struct Geo {
   int stride, ks, taps, nq, Hp, Wp, Ho, Wo, center, L, Lpad, Npad, Cin16, SC, SW, KB, cg, ngroups, nblk, nsteps;
@@ -91,7 +92,7 @@ bool geo_ok(const Geo& g, int H, int W, int Cin, int Cout, int ks, int stride) {
   if (!((ks == 3 && (stride == 1 || stride == 2)) || (ks == 1 && stride == 1))) return false;
   if (stride == 2 && ((H | W) & 1)) return false;
   return Cin <= 256 && Cout <= 256 && (Cout % 2) == 0 && (Cin % 2) == 0 && g.ngroups <= MAXG && g.Lpad <= MAX_LPAD &&
-         g.Mv < (1L << 31) && (g.w_resident || g.wst >= 2) && g.smem <= 227 * 1024 && (g.cg / g.V) <= MAX_UNITS;
+         g.Mv < (1L << 31) && (g.w_resident || g.wst >= 2) && g.smem <= 227 * 1024 && (g.cg / g.V) <= MAX_UNITS && g.nsteps <= MAX_STEPS;
 }
 
 struct TcParams {
@@ -106,6 +107,11 @@ struct TcParams {
   int B, H, W, Cin, Cout;
   long long* dbg;
   Geo g;
+  // host-built issue schedule: steps ordered (group, tap, K16 step); x = byte offset of the A operand inside a stage,
+  // y = weight slab index.  The MMA warp reads it from the constant bank (uniform loads): the issue loop must stay lean,
+  // a tcgen05.mma of N<=64 retires in ~40-48 cycles (measured) and integer address math per step would dominate.
+  int gcount[MAXG];
+  uint2 steps[MAX_STEPS];
 };
 
 // tap -> parity plane (stride 2) and row offset into the staged halo
@@ -117,6 +123,28 @@ __host__ __device__ __forceinline__ void tap_info(const Geo& g, int tap, int& q,
     const int py = (r == 1) ? 0 : 1, px = (s == 1) ? 0 : 1;
     q = py * 2 + px;
     rowoff = ((r == 0) ? 0 : 1) * g.Wp + ((s == 0) ? 0 : 1);
+  }
+}
+
+void build_steps(TcParams& p) {
+  const Geo& g = p.g;
+  const int nj = g.Cin16 / 16;
+  int n = 0;
+  for (int grp = 0; grp < g.ngroups; ++grp) {
+    const int c_lo = grp * g.cg, c_hi = c_lo + g.cg;
+    p.gcount[grp] = 0;
+    for (int tap = 0; tap < g.taps; ++tap) {
+      int q, rowoff;
+      tap_info(g, tap, q, rowoff);
+      for (int j = 0; j < nj; ++j) {
+        const int cs = q * g.Cin16 + 16 * j;
+        if (cs < c_lo || cs >= c_hi) continue;
+        const int cl = cs - c_lo;
+        p.steps[n].x = (uint32_t)(cl / g.KB) * (uint32_t)g.plane_bytes + (uint32_t)rowoff * g.SW + (uint32_t)(cl % g.KB) * 2;
+        p.steps[n].y = (uint32_t)(tap * nj + j);
+        ++n; ++p.gcount[grp];
+      }
+    }
   }
 }
 
@@ -226,21 +254,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
       } else {
         long it = 0;
         for (int ti = 0; ti < my_tiles; ++ti)
-          for (int grp = 0; grp < g.ngroups; ++grp) {
-            const int c_lo = grp * g.cg, c_hi = c_lo + g.cg;
-            for (int tap = 0; tap < g.taps; ++tap) {
-              int q, rowoff;
-              tap_info(g, tap, q, rowoff);
-              for (int j = 0; j < nj; ++j) {
-                const int cs = q * g.Cin16 + 16 * j;
-                if (cs < c_lo || cs >= c_hi) continue;
-                const int s = (int)(it % g.wst);
-                mbar_wait(BAR(32 + s), (uint32_t)(((it / g.wst) & 1) ^ 1));
-                mbar_expect_tx(BAR(16 + s), wslab);
-                tma_bulk_g2s(smem_u32(Wbase + (size_t)s * wslab), p.wpack + (size_t)(tap * nj + j) * wslab, wslab, BAR(16 + s));
-                ++it;
-              }
-            }
+          for (int st = 0; st < g.nsteps; ++st, ++it) {
+            const int s = (int)(it % g.wst);
+            mbar_wait(BAR(32 + s), (uint32_t)(((it / g.wst) & 1) ^ 1));
+            mbar_expect_tx(BAR(16 + s), wslab);
+            tma_bulk_g2s(smem_u32(Wbase + (size_t)s * wslab), p.wpack + (size_t)p.steps[st].y * wslab, wslab, BAR(16 + s));
           }
       }
     }
@@ -261,7 +279,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
       c_acc += clock64() - tq;
       tc_fence_after();
       const uint32_t d = tmem + (uint32_t)(as * g.acc_cols);
-      uint32_t first = 1;
+      uint32_t first = 0;                 // accumulate flag of the next MMA (0 = overwrite: first MMA of the tile)
+      int sidx = 0;
       for (int grp = 0; grp < g.ngroups; ++grp, ++f) {
         const int s = (int)(f % g.nastage);
         tq = clock64();
@@ -269,40 +288,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
         c_a += clock64() - tq;
         tc_fence_after();
         const uint32_t ab = a0 + (uint32_t)s * (uint32_t)g.a_stage_bytes;
-        const int c_lo = grp * g.cg, c_hi = c_lo + g.cg;
-        for (int tap = 0; tap < g.taps; ++tap) {
-          int q, rowoff;
-          tap_info(g, tap, q, rowoff);
-          for (int j = 0; j < nj; ++j) {
-            const int cs = q * g.Cin16 + 16 * j;                          // staged channel of this K step
-            if (cs < c_lo || cs >= c_hi) continue;
-            uint32_t wb;
-            int rs = 0;
-            if (g.w_resident) {
-              wb = w0 + (uint32_t)(tap * nj + j) * wslab;                 // slab index (pack order: tap-major)
-            } else {
-              rs = (int)(it % g.wst);
-              mbar_wait(BAR(16 + rs), (uint32_t)((it / g.wst) & 1));
-              tc_fence_after();
-              wb = w0 + (uint32_t)rs * wslab;
-            }
-            const int cl = cs - c_lo;
-            const uint32_t arow = ab + (uint32_t)(cl / g.KB) * plane + (uint32_t)rowoff * SW + (uint32_t)(cl % g.KB) * 2;
-            const uint64_t ah = with_addr(a_t, arow), al = with_addr(a_t, arow + lo_off);
-            const uint64_t bw = with_addr(b_t, wb), bl = with_addr(b_t, wb + (uint32_t)g.Npad * 16);
-            if (elect_one()) {
+        const int n = p.gcount[grp];
+        if (g.w_resident) {
+          if (elect_one()) {
+            for (int k = 0; k < n; ++k, ++sidx) {
+              const uint2 stp = p.steps[sidx];
+              const uint32_t arow = ab + stp.x, wb = w0 + stp.y * wslab;
+              const uint64_t ah = a_t | (uint64_t)(arow >> 4), al = a_t | (uint64_t)((arow + lo_off) >> 4);
+              const uint64_t bw = b_t | (uint64_t)(wb >> 4);
               if (g.concat) {
-                umma_bf16(d, ah, bw, idesc_2n, first ? 0u : 1u);           // [A_hi*w_hi | A_hi*w_lo]
-                umma_bf16(d, al, bw, idesc_n, 1u);                         // += A_lo*w_hi  (first Np rows of the slab)
+                umma_bf16(d, ah, bw, idesc_2n, first);                      // [A_hi*w_hi | A_hi*w_lo]
+                umma_bf16(d, al, bw, idesc_n, 1u);                          // += A_lo*w_hi (first Np rows of the slab)
               } else {
-                umma_bf16(d, ah, bw, idesc_n, first ? 0u : 1u);
-                umma_bf16(d, ah, bl, idesc_n, 1u);
+                umma_bf16(d, ah, bw, idesc_n, first);
+                umma_bf16(d, ah, bw + (uint64_t)(g.Npad), idesc_n, 1u);     // lo rows start Npad*16 bytes further
                 umma_bf16(d, al, bw, idesc_n, 1u);
               }
-              if (!g.w_resident) umma_commit(BAR(32 + rs));
+              first = 1u;
             }
-            first = 0;
-            ++it;
+          } else {
+            sidx += n;
+          }
+          first = 1u;
+        } else {
+          for (int k = 0; k < n; ++k, ++sidx, ++it) {
+            const int rs = (int)(it % g.wst);
+            mbar_wait(BAR(16 + rs), (uint32_t)((it / g.wst) & 1));
+            tc_fence_after();
+            const uint2 stp = p.steps[sidx];
+            const uint32_t arow = ab + stp.x, wb = w0 + (uint32_t)rs * wslab;
+            const uint64_t ah = a_t | (uint64_t)(arow >> 4), al = a_t | (uint64_t)((arow + lo_off) >> 4);
+            const uint64_t bw = b_t | (uint64_t)(wb >> 4);
+            if (elect_one()) {
+              if (g.concat) {
+                umma_bf16(d, ah, bw, idesc_2n, first);
+                umma_bf16(d, al, bw, idesc_n, 1u);
+              } else {
+                umma_bf16(d, ah, bw, idesc_n, first);
+                umma_bf16(d, ah, bw + (uint64_t)(g.Npad), idesc_n, 1u);
+                umma_bf16(d, al, bw, idesc_n, 1u);
+              }
+              umma_commit(BAR(32 + rs));
+            }
+            first = 1u;
           }
         }
         if (elect_one()) umma_commit(BAR(2 + s));                         // staged A buffer free
@@ -555,6 +583,7 @@ int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, 
   p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.in_relu = in_relu;
   p.wpack = reinterpret_cast<const uint8_t*>(wpack); p.bias = bias; p.y = y; p.accumulate = accumulate;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  build_steps(p);
   static long long* dbg = nullptr;
   static int dbg_on = -1;
   if (dbg_on < 0) {

@@ -29,6 +29,17 @@ __global__ void __launch_bounds__(128) bench(int N, int reps, int mode, long lon
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 96 * 1024);
     const uint32_t idesc = instr_desc(N);
     long long t0 = clock64();
+    if (mode & 8) {
+      // lean issue: descriptors precomputed, 8 MMAs per loop iteration, no per-MMA integer math
+      uint64_t ad[4], bd = sw128_desc(b0);
+      for (int k = 0; k < 4; ++k) ad[k] = sw128_desc(a0 + (uint32_t)k * 3072u);
+      if (elect_one()) {
+        for (int i = 0; i < reps; i += 8) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) umma_bf16(tmem + (uint32_t)((k % 3) * N % 256), ad[k & 3], bd, idesc, 1u);
+        }
+      }
+    } else
     for (int i = 0; i < reps; ++i) {
       const uint32_t ashift = (mode & 4) ? (uint32_t)(i % 9) * 1024u * 3u : 0u;
       uint64_t ad, bd;
@@ -53,9 +64,9 @@ int main() {
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int reps = 3000;
   for (int grid : {148})
-    for (int mode : {1, 7})
+    for (int mode : {1, 9})
       for (int N : {16, 32, 64, 128, 256}) {
-        if ((mode & 2) && 3 * N > 512) continue;
+        if ((mode & 2) && !(mode & 8) && 3 * N > 512) continue;
         bench<<<grid, 128, 200 * 1024>>>(N, reps, mode, out);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[148];
