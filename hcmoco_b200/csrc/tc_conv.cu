@@ -30,7 +30,8 @@ constexpr int NTHREADS = NTRANS + 128 + 64;  // then 4 epilogue warps, the TMA p
 constexpr int W_EPI = NTRANS / 32, W_TMA = W_EPI + 4, W_MMA = W_TMA + 1;
 constexpr int MAXG = 8;
 constexpr int MAX_LPAD = 512;
-constexpr int HDR_BYTES = 4096 + 2 * MAX_LPAD * 4 * 4 + 1024;   // barriers/tmem ptr/scale/shift | 2 src tables [Lpad][4] | unit table
+constexpr int HDR_BYTES = 4096 + 4096;      // barriers / tmem ptr / scale / shift | 4 per-team unit tables; the per-stage source tables follow
+constexpr int MAX_ASTAGE = 4;
 constexpr int MAX_UNITS = 256;
 constexpr int MAX_STEPS = 144;                // 9 taps x 256/16 channels
 
@@ -38,7 +39,7 @@ struct Geo {
   int stride, ks, taps, nq, Hp, Wp, Ho, Wo, center, L, Lpad, Npad, Cin16, SC, SW, KB, cg, ngroups, nblk, nsteps;
   int concat, acc_cols, acc_stages, tmem_cols, nastage, w_resident, wst, spb, grid, V;
   long Mv, tiles;
-  size_t plane_bytes, a_stage_bytes, wslab, wbytes, smem;
+  size_t plane_bytes, a_stage_bytes, wslab, wbytes, smem, tab_bytes;
 };
 
 Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride) {
@@ -77,9 +78,18 @@ Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride) {
   g.tmem_cols = c;
   g.wslab = (size_t)64 * g.Npad;              // [2 K-chunks][2*Npad rows: hi then lo][16 B]
   g.wbytes = (size_t)g.nsteps * g.wslab;
-  const size_t budget = 224 * 1024 - HDR_BYTES;
+  // A stages: each is filled by its own team of transform warps, so several halo gathers are in flight at once (the
+  // gather of a narrow layer is pure latency: ~5 loads per thread); 2..4 stages as shared memory allows
+  const size_t tab1 = (size_t)ceil_to(g.Lpad * g.nq * 4, 1024);           // source-pixel table of one stage
   const size_t wmin = g.wbytes < 8 * g.wslab ? g.wbytes : 8 * g.wslab;
-  g.nastage = (2 * g.a_stage_bytes + wmin <= budget) ? 2 : 1;
+  const size_t total = 225 * 1024 - HDR_BYTES;
+  g.nastage = 1;
+  for (int n = MAX_ASTAGE; n >= 2; n >>= 1) {      // 4 or 2: teams of NTRANS/n threads (whole warps)
+    const size_t w = (g.wbytes + n * (g.a_stage_bytes + tab1) <= total) ? g.wbytes : wmin;   // prefer resident weights
+    if (n * (g.a_stage_bytes + tab1) + w <= total && (n == 2 || g.wbytes + n * (g.a_stage_bytes + tab1) <= total)) { g.nastage = n; break; }
+  }
+  g.tab_bytes = g.nastage * tab1;
+  const size_t budget = total - g.tab_bytes;
   const size_t left_b = budget > g.nastage * g.a_stage_bytes ? budget - g.nastage * g.a_stage_bytes : 0;
   g.w_resident = g.wbytes <= left_b ? 1 : 0;
   // ring: one barrier per chunk of `spb` consecutive schedule steps (an mbarrier wait costs ~90 cycles: per-step waits
@@ -95,7 +105,7 @@ Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride) {
     const size_t slots = left_b / (spb * g.wslab);
     g.wst = (int)(slots > 16 ? 16 : slots);
   }
-  g.smem = HDR_BYTES + g.nastage * g.a_stage_bytes + (g.w_resident ? g.wbytes : (size_t)g.wst * g.spb * g.wslab);
+  g.smem = HDR_BYTES + g.tab_bytes + g.nastage * g.a_stage_bytes + (g.w_resident ? g.wbytes : (size_t)g.wst * g.spb * g.wslab);
   g.grid = (int)(g.tiles < 148 ? g.tiles : 148);
   return g;
 }
@@ -210,14 +220,15 @@ __device__ __forceinline__ uint64_t with_addr(uint64_t templ, uint32_t saddr) { 
 __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Geo& g = p.g;
-  // barriers: 0,1 a_full  2,3 a_empty  4,5 acc_full  6,7 acc_empty  8 w_full(resident)  16..31 ring full, 32..47 ring empty
+  // barriers: 0..3 a_full  4..7 a_empty  8,9 acc_full  10,11 acc_empty  12 w_full(resident)  16..31 ring full, 32..47 ring empty
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + 512);
   float* s_sc = reinterpret_cast<float*>(smem + 1024);
   float* s_sh = s_sc + 256;
-  int* s_src = reinterpret_cast<int*>(smem + 4096);                      // [2 stages][MAX_LPAD][4 planes]
-  int* s_unit = reinterpret_cast<int*>(smem + 4096 + 2 * MAX_LPAD * 16); // per group: packed (q, src channel, staged byte)
-  uint8_t* Abase = smem + HDR_BYTES;
+  int* s_unit = reinterpret_cast<int*>(smem + 4096);                     // per group: packed (q, src channel, staged byte)
+  int* s_src = reinterpret_cast<int*>(smem + HDR_BYTES);                 // [nastage][Lpad][nq] source pixel or -1
+  const int tab_stride = (int)(g.tab_bytes / g.nastage / 4);
+  uint8_t* Abase = smem + HDR_BYTES + g.tab_bytes;
   const uint32_t SW = (uint32_t)g.SW;
   const uint32_t plane = (uint32_t)g.plane_bytes;
   const uint32_t lo_off = (uint32_t)g.nblk * plane;                      // A_lo planes follow the A_hi planes of a stage
@@ -229,11 +240,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
   if (threadIdx.x == 0) {
-    mbar_init(BAR(0), NTRANS); mbar_init(BAR(1), NTRANS);
-    mbar_init(BAR(2), 1); mbar_init(BAR(3), 1);
-    mbar_init(BAR(4), 1); mbar_init(BAR(5), 1);
-    mbar_init(BAR(6), 128); mbar_init(BAR(7), 128);
-    mbar_init(BAR(8), 1);
+    for (int s = 0; s < MAX_ASTAGE; ++s) { mbar_init(BAR(s), NTRANS / g.nastage); mbar_init(BAR(4 + s), 1); }
+    mbar_init(BAR(8), 1); mbar_init(BAR(9), 1);
+    mbar_init(BAR(10), 128); mbar_init(BAR(11), 128);
+    mbar_init(BAR(12), 1);
     for (int s = 0; s < 16; ++s) { mbar_init(BAR(16 + s), 1); mbar_init(BAR(32 + s), 1); }
     fence_mbar_init();
   }
@@ -258,10 +268,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     // ===== TMA producer: weight slabs in the order the MMA warp consumes them =====
     if (lane == 0) {
       if (g.w_resident) {
-        mbar_expect_tx(BAR(8), (uint32_t)g.wbytes);
+        mbar_expect_tx(BAR(12), (uint32_t)g.wbytes);
         for (size_t off = 0; off < g.wbytes; off += 32768) {
           const uint32_t n = (uint32_t)(g.wbytes - off < 32768 ? g.wbytes - off : 32768);
-          tma_bulk_g2s(smem_u32(Wbase + off), p.wpack + off, n, BAR(8));
+          tma_bulk_g2s(smem_u32(Wbase + off), p.wpack + off, n, BAR(12));
         }
       } else {
         long it = 0;                                                     // chunk counter
@@ -286,12 +296,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     const uint32_t b_lbo = (uint32_t)(2 * g.Npad) * 16;
     const uint64_t b_t = smem_desc(0, b_lbo, 128);                         // no-swizzle K-major weight slab
     long long c_acc = 0, c_a = 0, c_all = clock64(), tq;
-    if (g.w_resident) mbar_wait(BAR(8), 0);
-    long it = 0, f = 0;
+    if (g.w_resident) mbar_wait(BAR(12), 0);
+    long f = 0;
+    int within = 0, rs = 0;          // weight ring: step inside the current chunk, slot, slot phase
+    uint32_t rph = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int as = ti % g.acc_stages;
       tq = clock64();
-      mbar_wait(BAR(6 + as), (uint32_t)(((ti / g.acc_stages) & 1) ^ 1));  // epilogue has drained this accumulator
+      mbar_wait(BAR(10 + as), (uint32_t)(((ti / g.acc_stages) & 1) ^ 1)); // epilogue has drained this accumulator
       c_acc += clock64() - tq;
       tc_fence_after();
       const uint32_t d = tmem + (uint32_t)(as * g.acc_cols);
@@ -328,10 +340,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
           first = 1u;
         } else {
           for (int k = 0; k < n; ++k, ++sidx) {
-            const int within = sidx % g.spb;                               // position inside the current ring chunk
-            const int rs = (int)(it % g.wst);
             if (within == 0 || k == 0) {
-              mbar_wait(BAR(16 + rs), (uint32_t)((it / g.wst) & 1));      // (re-waiting a completed phase is harmless)
+              mbar_wait(BAR(16 + rs), rph);                                // (re-waiting a completed phase is harmless)
               tc_fence_after();
             }
             const uint2 stp = p.steps[sidx];
@@ -350,13 +360,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
               }
               if (last) umma_commit(BAR(32 + rs));
             }
-            if (last) ++it;
+            if (last) { within = 0; if (++rs == g.wst) { rs = 0; rph ^= 1u; } } else { ++within; }
             first = 1u;
           }
         }
-        if (elect_one()) umma_commit(BAR(2 + s));                         // staged A buffer free
+        if (elect_one()) umma_commit(BAR(4 + s));                         // staged A buffer free
       }
-      if (elect_one()) umma_commit(BAR(4 + as));                          // accumulator complete
+      if (elect_one()) umma_commit(BAR(8 + as));                          // accumulator complete
     }
     if (p.dbg && lane == 0) {
       long long* o = p.dbg + (long)blockIdx.x * 16;
@@ -364,21 +374,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     }
   } else if (warp < W_EPI) {
     // ===== transform warps: coalesced gather + BN/ReLU-on-load + bf16 split -> swizzled channels-last tile =====
-    const int t = threadIdx.x;
+    const int TS = NTRANS / g.nastage;                                    // team size: team k owns A stage k
+    const int team = threadIdx.x / TS, t = threadIdx.x - team * TS;
     const int V = g.V;
-    long f = 0;
     long long c_wait = 0, c_all = clock64(), tq;
-    for (int ti = 0; ti < my_tiles; ++ti) {
-      const long tile0 = ((long)blockIdx.x + (long)ti * gridDim.x) * TILE_M;
-      for (int grp = 0; grp < g.ngroups; ++grp, ++f) {
-        const int s = (int)(f % g.nastage);
+    const long nfills = (long)my_tiles * g.ngroups;
+    for (long f = team; f < nfills; f += g.nastage) {
+      {
+        const int ti = (int)(f / g.ngroups), grp = (int)(f - (long)ti * g.ngroups);
+        const long tile0 = ((long)blockIdx.x + (long)ti * gridDim.x) * TILE_M;
+        const int s = team;
         tq = clock64();
-        mbar_wait(BAR(2 + s), (uint32_t)(((f / g.nastage) & 1) ^ 1));
+        mbar_wait(BAR(4 + s), (uint32_t)(((f / g.nastage) & 1) ^ 1));
         c_wait += clock64() - tq;
-        int* src_tab = s_src + s * MAX_LPAD * 4;
-        for (int e = t; e < g.Lpad * g.nq; e += NTRANS) {
+        int* src_tab = s_src + s * tab_stride;
+        for (int e = t; e < g.Lpad * g.nq; e += TS) {
           const int pos = e / g.nq, q = e - pos * g.nq;
-          src_tab[pos * 4 + q] = (pos < g.L) ? virt_to_src(tile0 - g.center + pos, q, p) : -1;
+          src_tab[e] = (pos < g.L) ? virt_to_src(tile0 - g.center + pos, q, p) : -1;
         }
         // unit table of this group: the real (non-padding) channel units [V channels] it stages
         const int c_lo = grp * g.cg, c_hi = c_lo + g.cg;
@@ -387,7 +399,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
           const int a = max(c_lo, q * g.Cin16), b = min(c_hi, q * g.Cin16 + p.Cin);
           if (b > a) upp += (b - a) / V;
         }
-        if (ti == 0 || g.ngroups > 1) {
+        {
           if (t < upp) {
             int rem = t, q = 0, cs = 0;
             for (q = 0; q < g.nq; ++q) {
@@ -398,27 +410,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
             }
             const int csrc = cs - q * g.Cin16, cl = cs - c_lo;
             // packed: plane q (2 bits) | source channel (10 bits) | staged block (4 bits) | byte within row block (8 bits)
-            s_unit[t] = q | (csrc << 2) | ((cl / g.KB) << 12) | (((cl % g.KB) * 2) << 16);
+            s_unit[team * MAX_UNITS + t] = q | (csrc << 2) | ((cl / g.KB) << 12) | (((cl % g.KB) * 2) << 16);
           }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(NTRANS) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TS) : "memory");
         uint8_t* A_hi = Abase + (size_t)s * g.a_stage_bytes;
         const int total = upp * g.Lpad;
-        const int dpos = NTRANS / upp, drc = NTRANS - dpos * upp;
+        const int dpos = TS / upp, drc = TS - dpos * upp;
         int pos = t / upp, rc = t - pos * upp;
-        for (int e0 = t; e0 < total; e0 += 4 * NTRANS) {
+        for (int e0 = t; e0 < total; e0 += 4 * TS) {
           float v[4][4];
           uint32_t dst[4];
           int csrcv[4];
           bool act[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            act[u] = (e0 + u * NTRANS) < total;
-            const int un = s_unit[act[u] ? rc : 0];
+            act[u] = (e0 + u * TS) < total;
+            const int un = s_unit[team * MAX_UNITS + (act[u] ? rc : 0)];
             const int q = un & 3, csrc = (un >> 2) & 1023;
             csrcv[u] = csrc;
             dst[u] = (uint32_t)((un >> 12) & 15) * plane + swz((uint32_t)(act[u] ? pos : 0), (uint32_t)(un >> 16), SW);
-            const int px = act[u] ? src_tab[pos * 4 + q] : -1;
+            const int px = act[u] ? src_tab[pos * g.nq + q] : -1;
             v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
             if (px >= 0) {
               const float* xp = p.x + (long)px * p.Cin + csrc;
@@ -432,7 +444,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
             } else {
               csrcv[u] = -1;
             }
-            // advance (pos, rc) by NTRANS units
+            // advance (pos, rc) by TS units
             pos += dpos; rc += drc;
             if (rc >= upp) { rc -= upp; ++pos; }
           }
@@ -470,7 +482,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
         mbar_arrive(BAR(s));
       }
     }
-    if (p.dbg && t == 0) { long long* o = p.dbg + (long)blockIdx.x * 16; o[4] = clock64() - c_all; o[5] = c_wait; }
+    if (p.dbg && threadIdx.x == 0) { long long* o = p.dbg + (long)blockIdx.x * 16; o[4] = clock64() - c_all; o[5] = c_wait; }
   } else {
     // ===== epilogue warps: TMEM -> registers -> global (fp32 NHWC), interior positions only =====
     const int q = warp & 3;                             // TMEM lane quarter this warp may access
@@ -483,7 +495,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
       const int px = virt_to_dst(tile0 + m, p);
       float* yp = p.y + (long)(px < 0 ? 0 : px) * p.Cout;
       tq = clock64();
-      mbar_wait(BAR(4 + as), (uint32_t)((ti / g.acc_stages) & 1));
+      mbar_wait(BAR(8 + as), (uint32_t)((ti / g.acc_stages) & 1));
       c_wait += clock64() - tq;
       tc_fence_after();
       for (int c0 = 0; c0 < g.Npad; c0 += 16) {
@@ -523,7 +535,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
         }
       }
       tc_fence_before();
-      mbar_arrive(BAR(6 + as));                         // accumulator stage may be overwritten
+      mbar_arrive(BAR(10 + as));                        // accumulator stage may be overwritten
     }
     if (p.dbg && m == 0) { long long* o = p.dbg + (long)blockIdx.x * 16; o[6] = clock64() - c_all; o[7] = c_wait; }
   }
