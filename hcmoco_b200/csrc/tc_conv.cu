@@ -36,14 +36,17 @@ constexpr int MAX_UNITS = 256;
 constexpr int MAX_STEPS = 144;                // 9 taps x 256/16 channels
 
 struct Geo {
+  int mode;          // 0: convolution; 1: data gradient of a 3x3 stride-2 convolution (see hcm_tc_dgrad_s2)
+  int Cp;            // mode 1: padded original Cin = width of one output parity block
   int stride, ks, taps, nq, Hp, Wp, Ho, Wo, center, L, Lpad, Npad, Cin16, SC, SW, KB, cg, ngroups, nblk, nsteps;
   int concat, acc_cols, acc_stages, tmem_cols, nastage, w_resident, wst, spb, grid, V;
   long Mv, tiles;
   size_t plane_bytes, a_stage_bytes, wslab, wbytes, smem, tab_bytes;
 };
 
-Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride) {
+Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride, int mode = 0) {
   Geo g;
+  g.mode = mode; g.Cp = 0;
   g.stride = stride; g.ks = ks; g.taps = ks * ks;
   g.nq = (stride == 2) ? 4 : 1;
   g.Ho = (stride == 2) ? H / 2 : H;
@@ -51,10 +54,17 @@ Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride) {
   if (ks == 1) { g.Hp = H; g.Wp = W; g.center = 0; g.L = TILE_M; }
   else if (stride == 1) { g.Hp = H + 2; g.Wp = W + 2; g.center = g.Wp + 1; g.L = TILE_M + 2 * (g.Wp + 1); }
   else { g.Hp = g.Ho + 1; g.Wp = g.Wo + 1; g.center = g.Wp + 1; g.L = TILE_M + g.Wp + 1; }
+  if (mode == 1) {
+    // H, W are the OUTPUT (= conv input) size; the staged tensor is dy [B,H/2,W/2,Cin]; virtual grid padded bottom/right
+    g.stride = 1; g.ks = 2; g.taps = 4; g.nq = 1;
+    g.Ho = H / 2; g.Wo = W / 2;
+    g.Hp = g.Ho + 1; g.Wp = g.Wo + 1; g.center = 0; g.L = TILE_M + g.Wp + 1;
+    g.Cp = ceil_to(Cout, 16);
+  }
   g.Mv = (long)B * g.Hp * g.Wp;
   g.tiles = (g.Mv + TILE_M - 1) / TILE_M;
   g.Lpad = ceil_to(g.L, 16);
-  g.Npad = ceil_to(Cout, 16);
+  g.Npad = (mode == 1) ? 4 * g.Cp : ceil_to(Cout, 16);
   g.Cin16 = ceil_to(Cin, 16);
   g.SC = g.nq * g.Cin16;                      // staged channels per position
   g.V = (Cin % 4 == 0) ? 4 : 2;
@@ -139,7 +149,8 @@ struct TcParams {
 // tap -> parity plane (stride 2) and row offset into the staged halo
 __host__ __device__ __forceinline__ void tap_info(const Geo& g, int tap, int& q, int& rowoff) {
   const int r = tap / g.ks, s = tap - r * g.ks;
-  if (g.ks == 1) { q = 0; rowoff = 0; }
+  if (g.mode == 1) { q = 0; rowoff = r * g.Wp + s; }
+  else if (g.ks == 1) { q = 0; rowoff = 0; }
   else if (g.stride == 1) { q = 0; rowoff = r * g.Wp + s; }
   else {
     const int py = (r == 1) ? 0 : 1, px = (s == 1) ? 0 : 1;
@@ -174,10 +185,14 @@ void build_steps(TcParams& p) {
 __device__ __forceinline__ int virt_to_src(long pv, int q, const TcParams& p) {
   const Geo& g = p.g;
   if (pv < 0 || pv >= g.Mv) return -1;
-  if (g.ks == 1) return (int)pv;
+  if (g.mode == 0 && g.ks == 1) return (int)pv;
   const unsigned v = (unsigned)pv, hw = (unsigned)(g.Hp * g.Wp);
   const unsigned b = v / hw, rem = v - b * hw;
   const unsigned row = rem / (unsigned)g.Wp, col = rem - row * (unsigned)g.Wp;
+  if (g.mode == 1) {
+    if (row >= (unsigned)g.Ho || col >= (unsigned)g.Wo) return -1;
+    return (int)((b * g.Ho + row) * g.Wo + col);
+  }
   if (g.stride == 1) {
     if (row < 1 || row > (unsigned)p.H || col < 1 || col > (unsigned)p.W) return -1;
     return (int)((b * p.H + row - 1) * p.W + (col - 1));
@@ -190,10 +205,14 @@ __device__ __forceinline__ int virt_to_src(long pv, int q, const TcParams& p) {
 __device__ __forceinline__ int virt_to_dst(long pv, const TcParams& p) {
   const Geo& g = p.g;
   if (pv < 0 || pv >= g.Mv) return -1;
-  if (g.ks == 1) return (int)pv;
+  if (g.mode == 0 && g.ks == 1) return (int)pv;
   const unsigned v = (unsigned)pv, hw = (unsigned)(g.Hp * g.Wp);
   const unsigned b = v / hw, rem = v - b * hw;
   const unsigned row = rem / (unsigned)g.Wp, col = rem - row * (unsigned)g.Wp;
+  if (g.mode == 1) {
+    if (row >= (unsigned)g.Ho || col >= (unsigned)g.Wo) return -1;
+    return (int)((b * p.H + 2 * row) * p.W + 2 * col);
+  }
   if (row < 1 || col < 1 || row > (unsigned)g.Ho || col > (unsigned)g.Wo) return -1;
   return (int)((b * g.Ho + row - 1) * g.Wo + (col - 1));
 }
@@ -493,12 +512,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
       const long tile0 = ((long)blockIdx.x + (long)ti * gridDim.x) * TILE_M;
       const int as = ti % g.acc_stages;
       const int px = virt_to_dst(tile0 + m, p);
-      float* yp = p.y + (long)(px < 0 ? 0 : px) * p.Cout;
+      float* yp = p.y + (long)(px < 0 ? 0 : px) * p.Cout;   // indexed [c0 + i] below
       tq = clock64();
       mbar_wait(BAR(8 + as), (uint32_t)((ti / g.acc_stages) & 1));
       c_wait += clock64() - tq;
       tc_fence_after();
       for (int c0 = 0; c0 < g.Npad; c0 += 16) {
+        if (g.mode == 1) {
+          // parity block qq = c0 / Cp of the 2x2 output pixels of this position; channel offset inside the block
+          const int qq = c0 / g.Cp, cc = c0 - qq * g.Cp;
+          yp = p.y + ((long)(px < 0 ? 0 : px) + (long)(qq >> 1) * p.W + (qq & 1)) * p.Cout - c0 + cc;
+        }
         float v[16];
         const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * g.acc_cols + c0);
         tmem_ld16(tbase, v);
@@ -508,15 +532,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += u[i];
         }
+        const int cend = (g.mode == 1) ? (c0 / g.Cp) * g.Cp + p.Cout : p.Cout;      // first invalid column
         if (px >= 0) {
           if (p.bias) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) if (c0 + i < p.Cout) v[i] += p.bias[c0 + i];
+            for (int i = 0; i < 16; ++i) if (c0 + i < cend) v[i] += p.bias[c0 + i];
           }
           if (vec4) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
-              if (c0 + i < p.Cout) {
+              if (c0 + i < cend) {
                 float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                 if (p.accumulate) { const float4 old = *reinterpret_cast<const float4*>(yp + c0 + i); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
                 *reinterpret_cast<float4*>(yp + c0 + i) = o;
@@ -525,7 +550,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
           } else {
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
-              if (c0 + i < p.Cout) {
+              if (c0 + i < cend) {
                 float2 o = make_float2(v[i], v[i + 1]);
                 if (p.accumulate) { const float2 old = *reinterpret_cast<const float2*>(yp + c0 + i); o.x += old.x; o.y += old.y; }
                 *reinterpret_cast<float2*>(yp + c0 + i) = o;
@@ -571,9 +596,101 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, uint8_t* __restrict_
   }
 }
 
+// Data gradient of a 3x3 / stride-2 / pad-1 convolution as ONE 2x2-tap stride-1 GEMM over dy whose N axis is the four
+// output-pixel parities: slab(tap=(du,dv), K step j): B[n = q*Cp + ci][c = co] = w[co][ci][r][s] with
+// (py,du) -> r : (0,0)->1, (1,0)->2, (1,1)->0, (0,1)->none ; same for (px,dv) -> s.
+__global__ void tc_pack_dgrad2_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, Geo g, int CoutW, int CinW) {
+  const int nj = g.Cin16 / 16;
+  const int step = blockIdx.x;
+  const int tap = step / nj, j = step - tap * nj;
+  const int du = tap >> 1, dv = tap & 1;
+  uint8_t* slab = out + (size_t)step * g.wslab;
+  for (int e = threadIdx.x; e < g.Npad * 16; e += blockDim.x) {
+    const int n = e >> 4, k = e & 15;
+    const int q = n / g.Cp, ci = n - q * g.Cp;
+    const int py = q >> 1, px = q & 1;
+    const int r = (py == 0) ? (du == 0 ? 1 : -1) : (du == 0 ? 2 : 0);
+    const int sx = (px == 0) ? (dv == 0 ? 1 : -1) : (dv == 0 ? 2 : 0);
+    const int co = 16 * j + k;
+    float v = 0.f;
+    if (r >= 0 && sx >= 0 && ci < CinW && co < CoutW) v = w[(((long)co * CinW + ci) * 3 + r) * 3 + sx];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const size_t chunk = (size_t)(k >> 3) * (2 * g.Npad) * 16;
+    *reinterpret_cast<__nv_bfloat16*>(slab + chunk + (size_t)n * 16 + (k & 7) * 2) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(slab + chunk + (size_t)(g.Npad + n) * 16 + (k & 7) * 2) = lo;
+  }
+}
+
+bool dgrad2_ok(const Geo& g, int H, int W, int Cin, int Cout) {
+  return ((H | W) & 1) == 0 && (Cin % 2) == 0 && (Cout % 2) == 0 && Cout <= 256 && g.Npad <= 256 && g.ngroups <= MAXG &&
+         g.Lpad <= MAX_LPAD && g.Mv < (1L << 31) && (g.w_resident || g.wst >= 2) && g.smem <= 227 * 1024 &&
+         (g.cg / g.V) <= MAX_UNITS && g.nsteps <= MAX_STEPS;
+}
+
+int launch_tc(TcParams& p, cudaStream_t stream, const char* what) {
+  build_steps(p);
+  static long long* dbg = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    dbg_on = getenv("HCM_TC_DEBUG") ? 1 : 0;
+    if (dbg_on) cudaMalloc(&dbg, 148 * 16 * sizeof(long long));
+  }
+  p.dbg = dbg;
+  if (dbg_on) cudaMemsetAsync(dbg, 0, 148 * 16 * sizeof(long long), stream);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { hcm_set_error("%s: smem attribute: %s", what, cudaGetErrorString(e)); return HCM_ERR_CUDA; }
+    configured = true;
+  }
+  tc_conv_kernel<<<(unsigned)p.g.grid, NTHREADS, p.g.smem, stream>>>(p);
+  HCM_LAUNCH_CHECK(what);
+  if (dbg_on) {
+    long long h[148 * 16];
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long* o = h;      // CTA 0
+    fprintf(stderr, "[%s dbg] %dx%d %d->%d mode %d tiles/cta %ld steps %d astages %d resident %d | mma: total %lld wait_acc %lld "
+            "wait_a %lld | transform: total %lld wait %lld | epilogue: total %lld wait %lld\n", what, p.H, p.W, p.Cin, p.Cout,
+            p.g.mode, (p.g.tiles + p.g.grid - 1) / p.g.grid, p.g.nsteps, p.g.nastage, p.g.w_resident, o[0], o[2], o[3], o[4],
+            o[5], o[6], o[7]);
+  }
+  return HCM_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+// ---- data gradient of a 3x3 stride-2 pad-1 convolution w[Cout][Cin][3][3]: dx[B,H,W,Cin] (+)= conv_transpose(dy[B,H/2,W/2,Cout])
+int hcm_tc_dgrad_s2_supported(int B, int H, int W, int Cin, int Cout) {
+  if ((H | W) & 1) return 0;
+  Geo g = make_geo(B, H, W, Cout, Cin, 3, 2, 1);          // GEMM: K = Cout (channels of dy), N = 4 parities x Cin
+  return dgrad2_ok(g, H, W, Cout, Cin) ? 1 : 0;
+}
+long hcm_tc_dgrad_s2_wpack_bytes(int B, int H, int W, int Cin, int Cout) {
+  Geo g = make_geo(B, H, W, Cout, Cin, 3, 2, 1);
+  return (long)g.wbytes;
+}
+int hcm_tc_dgrad_s2_pack(const float* w, void* wpack, int B, int H, int W, int Cin, int Cout, cudaStream_t stream) {
+  HCM_CHECK_ARG(w && wpack, "tc_dgrad_s2_pack: null pointer");
+  Geo g = make_geo(B, H, W, Cout, Cin, 3, 2, 1);
+  HCM_CHECK_ARG(dgrad2_ok(g, H, W, Cout, Cin), "tc_dgrad_s2_pack: unsupported geometry");
+  tc_pack_dgrad2_kernel<<<g.nsteps, 256, 0, stream>>>(w, reinterpret_cast<uint8_t*>(wpack), g, Cout, Cin);
+  HCM_LAUNCH_CHECK("tc_dgrad_s2_pack");
+  return HCM_OK;
+}
+int hcm_tc_dgrad_s2(const float* dy, const void* wpack, float* dx, int B, int H, int W, int Cin, int Cout, int accumulate,
+                    cudaStream_t stream) {
+  HCM_CHECK_ARG(dy && wpack && dx, "tc_dgrad_s2: null pointer");
+  TcParams p;
+  p.g = make_geo(B, H, W, Cout, Cin, 3, 2, 1);
+  HCM_CHECK_ARG(dgrad2_ok(p.g, H, W, Cout, Cin), "tc_dgrad_s2: unsupported geometry (Cin=%d Cout=%d)", Cin, Cout);
+  p.x = dy; p.in_scale = nullptr; p.in_shift = nullptr; p.in_relu = 0;
+  p.wpack = reinterpret_cast<const uint8_t*>(wpack); p.bias = nullptr; p.y = dx; p.accumulate = accumulate;
+  p.B = B; p.H = H; p.W = W; p.Cin = Cout; p.Cout = Cin;   // as seen by the GEMM: staged channels = Cout(w), output channels = Cin(w)
+  return launch_tc(p, stream, "tc_dgrad_s2");
+}
 
 // 1 if hcm_tc_conv can run this convolution: 3x3 stride 1/2 (even H,W for stride 2) or 1x1 stride 1, even channels <= 256
 int hcm_tc_conv_supported(int B, int H, int W, int Cin, int Cout, int ks, int stride) {
@@ -616,32 +733,7 @@ int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, 
   p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.in_relu = in_relu;
   p.wpack = reinterpret_cast<const uint8_t*>(wpack); p.bias = bias; p.y = y; p.accumulate = accumulate;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-  build_steps(p);
-  static long long* dbg = nullptr;
-  static int dbg_on = -1;
-  if (dbg_on < 0) {
-    dbg_on = getenv("HCM_TC_DEBUG") ? 1 : 0;
-    if (dbg_on) cudaMalloc(&dbg, 148 * 16 * sizeof(long long));
-  }
-  p.dbg = dbg;
-  if (dbg_on) cudaMemsetAsync(dbg, 0, 148 * 16 * sizeof(long long), stream);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { hcm_set_error("tc_conv: smem attribute: %s", cudaGetErrorString(e)); return HCM_ERR_CUDA; }
-    configured = true;
-  }
-  tc_conv_kernel<<<(unsigned)p.g.grid, NTHREADS, p.g.smem, stream>>>(p);
-  HCM_LAUNCH_CHECK("tc_conv");
-  if (dbg_on) {
-    long long h[148 * 16];
-    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-    const long long* o = h;      // CTA 0
-    fprintf(stderr, "[tc_conv dbg] %dx%d %d->%d k%d s%d tiles/cta %ld steps %d | mma: total %lld wait_acc %lld wait_a %lld | "
-            "transform: total %lld wait %lld | epilogue: total %lld wait %lld\n", H, W, Cin, Cout, ks, stride,
-            (p.g.tiles + p.g.grid - 1) / p.g.grid, p.g.nsteps, o[0], o[2], o[3], o[4], o[5], o[6], o[7]);
-  }
-  return HCM_OK;
+  return launch_tc(p, stream, "tc_conv");
 }
 
 }  // extern "C"

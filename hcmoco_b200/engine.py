@@ -316,6 +316,10 @@ class Engine:
                     wp_t = K.empty((nbt + 3) // 4)
                     p.b(K.tc_conv_pack, w, 0, wp_t, B, H, W, cout, cin, ks, 1)
                     p.b(K.tc_conv, dy, wp_t, None, gx, B, H, W, cout, cin, ks, 1, None, None, 0, acc)
+                elif tc and stride == 2 and ks == 3 and K.tc_dgrad_s2_supported(B, H, W, cin, cout):
+                    wp_t = K.empty((K.tc_dgrad_s2_wpack_bytes(B, H, W, cin, cout) + 3) // 4)
+                    p.b(K.tc_dgrad_s2_pack, w, wp_t, B, H, W, cin, cout)
+                    p.b(K.tc_dgrad_s2, dy, wp_t, gx, B, H, W, cin, cout, acc)
                 else:
                     p.b(K.conv2d_dgrad, dy, w, gx, B, H, W, cin, cout, ks, stride, acc)
 
@@ -613,8 +617,10 @@ class Engine:
             o += ft.C
             ft.consumers += 1
             y = K.empty(B, ft.H, ft.W, 128)
-            if not (self.use_tc and K.tc_conv_supported(B, ft.H, ft.W, ft.C, 128, 1, 1)):
-                raise NotImplementedError("the 1x1 projection runs on the tensor-core path only")
+            # (the projection always runs on the tensor-core kernel, also in the exact-fp32 conv mode: its weight is a
+            #  strided column block of the checkpoint tensor, which only the tc pack / wgrad kernels address)
+            if not K.tc_conv_supported(B, ft.H, ft.W, ft.C, 128, 1, 1):
+                raise NotImplementedError("1x1 projection: unsupported geometry")
             wp = K.empty((K.tc_conv_wpack_bytes(B, ft.H, ft.W, ft.C, 128, 1) + 3) // 4)
             p.f(K.tc_conv_pack, ws[j], cm, wp, B, ft.H, ft.W, ft.C, 128, 1, 0)
             p.f(K.tc_conv, ft.data, wp, None, y, B, ft.H, ft.W, ft.C, 128, 1, 1, None, None, 0, 0)

@@ -60,6 +60,14 @@ int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, 
                 int ks, int stride, const float* in_scale, const float* in_shift, int in_relu, int accumulate,
                 cudaStream_t stream);
 
+/* data gradient of a 3x3 / stride-2 / pad-1 convolution w[Cout][Cin][3][3] on tensor cores (one 2x2-tap GEMM over dy whose
+ * N axis is the four output-pixel parities): dx[B,H,W,Cin] (+)= conv_transpose(dy[B,H/2,W/2,Cout], w) */
+int hcm_tc_dgrad_s2_supported(int B, int H, int W, int Cin, int Cout);
+long hcm_tc_dgrad_s2_wpack_bytes(int B, int H, int W, int Cin, int Cout);
+int hcm_tc_dgrad_s2_pack(const float* w, void* wpack, int B, int H, int W, int Cin, int Cout, cudaStream_t stream);
+int hcm_tc_dgrad_s2(const float* dy, const void* wpack, float* dx, int B, int H, int W, int Cin, int Cout, int accumulate,
+                    cudaStream_t stream);
+
 /* tensor-core weight gradient (tc_wgrad.cu): dw[Cout,Cin,ks,ks] += sum_pixels dy * T(x), stride 1 */
 int hcm_tc_wgrad_supported(int B, int H, int W, int Cin, int Cout, int ks, int stride);
 int hcm_tc_wgrad(const float* x, const float* dy, float* dw, int lddw, int B, int H, int W, int Cin, int Cout, int ks,

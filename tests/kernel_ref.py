@@ -130,6 +130,20 @@ class TorchKernels:
             y.reshape(-1).copy_(o)
         return 0
 
+    def tc_dgrad_s2_supported(self, B, H, W, Cin, Cout):
+        return int(H % 2 == 0 and W % 2 == 0 and Cin % 2 == 0 and Cout % 2 == 0 and Cin <= 64 and Cout <= 256)
+
+    def tc_dgrad_s2_wpack_bytes(self, B, H, W, Cin, Cout):
+        return Cin * Cout * 9 * 8
+
+    def tc_dgrad_s2_pack(self, w, wpack, B, H, W, Cin, Cout):
+        wpack.reshape(-1).view(w.dtype)[:Cin * Cout * 9].copy_(w.reshape(-1)[:Cin * Cout * 9])
+        return 0
+
+    def tc_dgrad_s2(self, dy, wpack, dx, B, H, W, Cin, Cout, accumulate):
+        w = wpack.reshape(-1).view(dy.dtype)[:Cin * Cout * 9]
+        return self.conv2d_dgrad(dy, w, dx, B, H, W, Cin, Cout, 3, 2, accumulate)
+
     def tc_wgrad_supported(self, B, H, W, Cin, Cout, ks, stride):
         return int(stride == 1 and self.tc_conv_supported(B, H, W, Cin, Cout, ks, stride))
 

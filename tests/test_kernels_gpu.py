@@ -392,3 +392,20 @@ def test_tc_conv_stride2(KK, shape):
     kc.tc_conv(x, wp, None, y1, B, H, W, Cin, Cout, 3, 2, None, None, 0, 0)
     kr.conv2d_fwd(x, w, None, y2, B, H, W, Cin, Cout, 3, 2, None, None, 0, None)
     assert rel(y1, y2) < 3e-5, rel(y1, y2)
+
+
+@pytest.mark.parametrize("shape", TC_S2)
+def test_tc_dgrad_stride2(KK, shape):
+    """data gradient of the stride-2 conv: one 2x2-tap GEMM over dy, N = 4 output parities x Cin."""
+    B, H, W, Cin, Cout = shape
+    kc, kr = KK
+    if not kc.tc_dgrad_s2_supported(B, H, W, Cin, Cout):
+        pytest.skip("N = 4*ceil16(Cin) > 256")
+    w, dy = rnd(Cout, Cin, 3, 3, scale=0.1), rnd(B, H // 2, W // 2, Cout, seed=3)
+    wp = torch.zeros((kc.tc_dgrad_s2_wpack_bytes(B, H, W, Cin, Cout) + 3) // 4, device=DEV)
+    kc.tc_dgrad_s2_pack(w, wp, B, H, W, Cin, Cout)
+    dx1, dx2 = rnd(B, H, W, Cin, seed=4), rnd(B, H, W, Cin, seed=4)
+    for acc in (0, 1):
+        kc.tc_dgrad_s2(dy, wp, dx1, B, H, W, Cin, Cout, acc)
+        kr.conv2d_dgrad(dy, w, dx2, B, H, W, Cin, Cout, 3, 2, acc)
+        assert rel(dx1, dx2) < 3e-5, (acc, rel(dx1, dx2))
