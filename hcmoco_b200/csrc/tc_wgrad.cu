@@ -36,7 +36,7 @@ WGeo make_wgeo(int B, int H, int W, int Cin, int Cout, int ks) {
   g.L = (ks == 3) ? TILE + 2 * (g.Wp + 1) : TILE;
   g.Lpad = ceil_to(g.L, 8);
   const int Cin16 = ceil_to(Cin, 16);
-  const int nr_max = (ks == 3) ? 48 : 256;
+  const int nr_max = (ks == 3) ? 48 : 128;
   g.nsplit = (Cin16 + nr_max - 1) / nr_max;
   g.Nr = ceil_to((Cin16 + g.nsplit - 1) / g.nsplit, 16);
   g.nblk = (Cout + 127) / 128;
