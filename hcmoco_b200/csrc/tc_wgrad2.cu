@@ -1,0 +1,395 @@
+// Tensor-core weight gradient (tcgen05 / TMEM, bf16 hi/lo split) of the 3x3 (stride 1 or 2) and 1x1 convolutions:
+//     dw[co][ci][r][s] += sum over output positions p of  dy[p][co] * T(x)[src(p, r, s)][ci]
+// the cuDNN wgrad behind nn.Conv2d backward (networks/official_hrnet/official_hrnet.py:26-29, 68-75, 187-216, 336-357).
+//
+// Same virtual flat position space and the same swizzled channels-last staged tiles as tc_conv.cu.  Per 128-position
+// tile the transform teams stage  dy -> Dy[pos][co]  (non-interior positions zeroed)  and  T(x) -> A[halo pos][ci]
+// (BN scale/shift(+ReLU) applied on load, padding zeroed; stride 2: four parity planes side by side).  Both are read
+// MN-major (channels contiguous, positions = K): one tcgen05.mma M=128 (co) x N x K=16 positions.
+// For stride 1 the three taps of a filter row are ONE MMA: the N blocks of the B operand are LBO = one staged row apart
+// (tap s+1 = next halo row), N = 3 x 32 channels; the accumulators D[co][tap*32 + ci] (288 TMEM columns) stay
+// resident while the CTA walks its range of tiles; the partial dw is added to global memory with fp32 atomics.
+// Grid = (tile ranges, splits of 32 (3x3) / 64 (1x1) input channels, output-channel blocks of 128).
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TILE = 128;
+constexpr int NTRANS = 512;
+constexpr int NTHREADS_W = NTRANS + 128 + 32;   // 16 transform warps, 4 epilogue warps, last warp: MMA issuer + TMEM owner
+constexpr int W_EPI = NTRANS / 32, W_MMA = W_EPI + 4;
+constexpr int HDR = 4096;
+constexpr int MAX_ASTAGE = 4;
+
+struct WGeo {
+  int stride, ks, taps, nq, Hp, Wp, Ho, Wo, center, L, Lpad;
+  int CI, nsplit, nblk, SWa, SWd, a_blocks, d_blocks, ntr, tiles_per, tmem_cols, nstage, Va, Vd;
+  long Mv, T;
+  size_t a_plane, d_plane, a_bytes, d_bytes, stage_bytes, tab_bytes, smem;
+};
+
+WGeo make_wgeo(int B, int H, int W, int Cin, int Cout, int ks, int stride) {
+  WGeo g;
+  g.stride = stride; g.ks = ks; g.taps = ks * ks;
+  g.nq = (stride == 2) ? 4 : 1;
+  g.Ho = (stride == 2) ? H / 2 : H;
+  g.Wo = (stride == 2) ? W / 2 : W;
+  if (ks == 1) { g.Hp = H; g.Wp = W; g.center = 0; g.L = TILE; }
+  else if (stride == 1) { g.Hp = H + 2; g.Wp = W + 2; g.center = g.Wp + 1; g.L = TILE + 2 * (g.Wp + 1); }
+  else { g.Hp = g.Ho + 1; g.Wp = g.Wo + 1; g.center = g.Wp + 1; g.L = TILE + g.Wp + 1; }
+  g.Mv = (long)B * g.Hp * g.Wp;
+  g.T = (g.Mv + TILE - 1) / TILE;
+  g.Lpad = ceil_to(g.L, 16);
+  g.CI = (ks == 3) ? 32 : 64;                          // input channels per CTA split
+  g.nsplit = (Cin + g.CI - 1) / g.CI;
+  g.nblk = (Cout + 127) / 128;
+  const int sc = g.nq * g.CI;                          // staged channels per halo row
+  g.SWa = (sc <= 32) ? 64 : 128;
+  g.a_blocks = (sc * 2 + g.SWa - 1) / g.SWa;
+  g.a_plane = (size_t)g.Lpad * g.SWa;
+  g.a_bytes = 2 * g.a_blocks * g.a_plane;              // hi + lo
+  const int cd16 = ceil_to(Cout < 128 ? Cout : 128, 16);
+  g.SWd = (cd16 <= 32) ? 64 : 128;
+  g.d_blocks = (cd16 * 2 + g.SWd - 1) / g.SWd;         // blocks actually staged (M=128 reads 256/SWd blocks)
+  g.d_plane = (size_t)TILE * g.SWd;
+  g.d_bytes = 2 * g.d_blocks * g.d_plane;
+  g.stage_bytes = g.d_bytes + g.a_bytes;
+  g.Va = (Cin % 4 == 0) ? 4 : 2;
+  g.Vd = (Cout % 4 == 0) ? 4 : 2;
+  int c = 32;
+  while (c < g.taps * g.CI) c <<= 1;
+  g.tmem_cols = c;
+  const size_t tab1 = (size_t)ceil_to((g.Lpad * g.nq + TILE) * 4, 1024);
+  // M=128 reads 256/SWd dy planes whatever Cout is (rows >= Cout are garbage and never read back): keep those reads in bounds
+  const size_t reach = (size_t)g.d_blocks * g.d_plane + (size_t)(256 / g.SWd) * g.d_plane;   // from the dy_lo start
+  const size_t slack = reach > g.stage_bytes ? reach - g.stage_bytes : 0;
+  const size_t total = 226 * 1024 - HDR - slack;
+  g.nstage = 1;
+  for (int n = MAX_ASTAGE; n >= 2; n >>= 1)
+    if (n * (g.stage_bytes + tab1) <= total) { g.nstage = n; break; }
+  g.tab_bytes = g.nstage * tab1;
+  g.smem = HDR + g.tab_bytes + g.nstage * g.stage_bytes + slack;
+  long want = 148L / ((long)g.nsplit * g.nblk);
+  if (want < 1) want = 1;
+  if (want > g.T) want = g.T;
+  g.tiles_per = (int)((g.T + want - 1) / want);
+  g.ntr = (int)((g.T + g.tiles_per - 1) / g.tiles_per);
+  return g;
+}
+
+bool wgeo_ok(const WGeo& g, int H, int W, int Cin, int Cout, int ks, int stride) {
+  if (!((ks == 3 && (stride == 1 || stride == 2)) || (ks == 1 && stride == 1))) return false;
+  if (stride == 2 && ((H | W) & 1)) return false;
+  return Cin <= 256 && Cout <= 256 && (Cin % 2) == 0 && (Cout % 2) == 0 && g.tmem_cols <= 512 && g.smem <= 227 * 1024 &&
+         g.Mv < (1L << 31) && g.Lpad <= 512;
+}
+
+struct WParams {
+  const float* x;
+  const float* in_scale;
+  const float* in_shift;
+  int in_relu;
+  const float* dy;
+  float* dw;
+  int B, H, W, Cin, Cout, lddw;
+  WGeo g;
+};
+
+__device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t kb, uint32_t SW) {
+  const uint32_t off = row * SW;
+  return off + ((((kb >> 4) ^ (off >> 7)) & (SW / 16 - 1)) << 4) + (kb & 15);
+}
+// MN-major swizzled operand descriptor: rows (K = positions) of SW bytes, 8-row groups SBO = 8*SW apart, MN blocks LBO apart
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t SW, uint32_t lbo_bytes) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(((8 * SW) >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(SW == 128 ? 2 : (SW == 64 ? 4 : 6)) << 61;
+  return d;
+}
+
+// virtual position -> input pixel of plane q (or -1), and -> output pixel (or -1); same grids as tc_conv.cu
+__device__ __forceinline__ void virt_decode(long pv, const WParams& p, int& src0, int& src1, int& src2, int& src3, int& dst) {
+  const WGeo& g = p.g;
+  src0 = src1 = src2 = src3 = dst = -1;
+  if (pv < 0 || pv >= g.Mv) return;
+  if (g.ks == 1) { src0 = (int)pv; dst = (int)pv; return; }
+  const unsigned v = (unsigned)pv, hw = (unsigned)(g.Hp * g.Wp);
+  const unsigned b = v / hw, rem = v - b * hw;
+  const unsigned row = rem / (unsigned)g.Wp, col = rem - row * (unsigned)g.Wp;
+  if (g.stride == 1) {
+    if (row < 1 || row > (unsigned)p.H || col < 1 || col > (unsigned)p.W) return;
+    src0 = (int)((b * p.H + row - 1) * p.W + (col - 1));
+    dst = src0;
+    return;
+  }
+  if (row < 1 || col < 1) return;
+  const unsigned yi = 2 * (row - 1), xi = 2 * (col - 1);
+  src0 = (int)((b * p.H + yi) * p.W + xi);
+  src1 = src0 + 1; src2 = src0 + p.W; src3 = src0 + p.W + 1;
+  dst = (int)((b * g.Ho + row - 1) * g.Wo + (col - 1));
+}
+
+// stage V channels (fp32 -> bf16 hi/lo) of one (row, channel) unit into a swizzled tile
+template <int V>
+__device__ __forceinline__ void put_unit(const float* v, uint8_t* hi_base, uint32_t lo_off, uint32_t dst) {
+  uint32_t h[2], l[2];
+#pragma unroll
+  for (int i = 0; i < V / 2; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  if (V == 4) {
+    *reinterpret_cast<uint2*>(hi_base + dst) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2*>(hi_base + lo_off + dst) = make_uint2(l[0], l[1]);
+  } else {
+    *reinterpret_cast<uint32_t*>(hi_base + dst) = h[0];
+    *reinterpret_cast<uint32_t*>(hi_base + lo_off + dst) = l[0];
+  }
+}
+
+// gather `nch` channels starting at c_first of `rows` positions into a swizzled tile; src_tab[row] = pixel or -1
+template <int V>
+__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int C, int c_first, int nch, int rows, const int* src_tab,
+                                           int tab_stride, int tab_off, uint8_t* hi_base, uint32_t lo_off, uint32_t plane, uint32_t SW,
+                                           uint32_t byte0, const float* s_sc, const float* s_sh, bool affine, int relu, int t, int TS) {
+  const int upp = nch / V;                               // units per row
+  const int total = upp * rows;
+  const int dpos = TS / upp, drc = TS - dpos * upp;
+  int pos = t / upp, rc = t - pos * upp;
+  for (int e0 = t; e0 < total; e0 += 4 * TS) {
+    float v[4][4];
+    uint32_t dst[4];
+    int cs[4];
+    bool act[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      act[u] = (e0 + u * TS) < total;
+      const int c = c_first + rc * V;
+      const uint32_t kb = byte0 + (uint32_t)(rc * V) * 2;              // byte inside the staged row (all blocks)
+      dst[u] = (kb / SW) * plane + swz((uint32_t)(act[u] ? pos : 0), kb % SW, SW);
+      const int px = act[u] ? src_tab[pos * tab_stride + tab_off] : -1;
+      cs[u] = (px >= 0) ? c : -1;
+      v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+      if (px >= 0) {
+        const float* xp = src + (long)px * C + c;
+        if (V == 4) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(xp));
+          v[u][0] = w4.x; v[u][1] = w4.y; v[u][2] = w4.z; v[u][3] = w4.w;
+        } else {
+          const float2 w2 = __ldg(reinterpret_cast<const float2*>(xp));
+          v[u][0] = w2.x; v[u][1] = w2.y;
+        }
+      }
+      pos += dpos; rc += drc;
+      if (rc >= upp) { rc -= upp; ++pos; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!act[u]) continue;
+      if (affine && cs[u] >= 0) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float a = fmaf(v[u][i], s_sc[cs[u] + i], s_sh[cs[u] + i]);
+          v[u][i] = relu ? fmaxf(a, 0.f) : a;
+        }
+      }
+      put_unit<V>(v[u], hi_base, lo_off, dst[u]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const WGeo& g = p.g;
+  // barriers: 0..3 full, 4..7 empty, 8 done
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + 512);
+  float* s_sc = reinterpret_cast<float*>(smem + 1024);
+  float* s_sh = s_sc + 256;
+  int* s_tab = reinterpret_cast<int*>(smem + HDR);           // per stage: [Lpad][nq] source pixels, then [128] output pixels
+  const int tab_stride = (int)(g.tab_bytes / g.nstage / 4);
+  uint8_t* Sbase = smem + HDR + g.tab_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+
+  const int ci_lo = blockIdx.y * g.CI;
+  const int ci_n = min(g.CI, p.Cin - ci_lo);                 // real input channels of this split
+  const int co_lo = blockIdx.z * 128;
+  const int co_n = min(128, p.Cout - co_lo);
+  const uint32_t SWa = (uint32_t)g.SWa, SWd = (uint32_t)g.SWd;
+  const uint32_t d_lo = (uint32_t)g.d_blocks * (uint32_t)g.d_plane;          // dy_lo planes follow dy_hi planes
+  const uint32_t a_off = (uint32_t)g.d_bytes;                                 // a-tile follows the dy tile in a stage
+  const uint32_t a_lo = (uint32_t)g.a_blocks * (uint32_t)g.a_plane;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_ASTAGE; ++s) { mbar_init(BAR(s), NTRANS / g.nstage); mbar_init(BAR(4 + s), 1); }
+    mbar_init(BAR(8), 1);
+    fence_mbar_init();
+  }
+  for (int c = threadIdx.x; c < 256; c += NTHREADS_W) {
+    s_sc[c] = (p.in_scale && c < p.Cin) ? p.in_scale[c] : 1.f;
+    s_sh[c] = (p.in_scale && c < p.Cin) ? p.in_shift[c] : 0.f;
+  }
+  // zero all staged tiles once (channel padding is never written afterwards and must read as 0)
+  for (size_t i = threadIdx.x; i < ((size_t)g.nstage * g.stage_bytes) / 16; i += NTHREADS_W)
+    reinterpret_cast<uint4*>(Sbase)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == W_MMA) tmem_alloc(smem_u32(tmem_ptr), g.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  const long t_beg = (long)blockIdx.x * g.tiles_per;
+  const long t_end = min(g.T, t_beg + g.tiles_per);
+  const int ntiles = (int)(t_end - t_beg);
+
+  if (warp == W_MMA) {
+    // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+    const uint32_t s0 = smem_u32(Sbase);
+    const uint64_t dy_t = mn_desc(0, SWd, (uint32_t)g.d_plane);
+    const bool concat = (g.stride == 1 && g.ks == 3);          // 3 taps of a filter row = N blocks one row apart
+    const uint64_t a_t = mn_desc(0, SWa, concat ? SWa : (uint32_t)g.a_plane);
+    const uint32_t idesc = instr_desc(concat ? 3 * g.CI : g.CI, 1);
+    const int nmma = concat ? 3 : g.taps;                       // MMAs per K step and pass
+    uint32_t* tap_boff = reinterpret_cast<uint32_t*>(smem + 3072);  // byte offset of the B operand / TMEM column per MMA
+    uint32_t* tap_col = tap_boff + 16;
+    for (int m = lane; m < 9; m += 32) {
+      tap_boff[m] = 0; tap_col[m] = 0;
+      if (m >= nmma) continue;
+      if (concat) { tap_boff[m] = (uint32_t)(m * g.Wp) * SWa; tap_col[m] = (uint32_t)(m * 3 * g.CI); }
+      else if (g.ks == 3) {
+        const int r = m / 3, sx = m - 3 * r;
+        const int q = ((r == 1) ? 0 : 2) + ((sx == 1) ? 0 : 1);
+        const uint32_t rows = (uint32_t)(((r == 0) ? 0 : 1) * g.Wp + ((sx == 0) ? 0 : 1));
+        const uint32_t kb = (uint32_t)(q * g.CI * 2);           // plane q = bytes [q*CI*2, (q+1)*CI*2) of the staged row
+        tap_boff[m] = rows * SWa + (kb / SWa) * (uint32_t)g.a_plane + (kb % SWa);
+        tap_col[m] = (uint32_t)(m * g.CI);
+      }
+    }
+    __syncwarp();
+    for (int it = 0; it < ntiles; ++it) {
+      const int s = it % g.nstage;
+      mbar_wait(BAR(s), (uint32_t)((it / g.nstage) & 1));
+      tc_fence_after();
+      const uint32_t st = s0 + (uint32_t)s * (uint32_t)g.stage_bytes;
+      for (int k = 0; k < TILE / 16; ++k) {
+        const uint32_t dyk = st + (uint32_t)k * 16u * SWd;
+        const uint64_t dyh = dy_t | (uint64_t)(dyk >> 4), dyl = dy_t | (uint64_t)((dyk + d_lo) >> 4);
+        const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+        const uint32_t abase = st + a_off + (uint32_t)k * 16u * SWa;
+        for (int m = 0; m < nmma; ++m) {
+          // operand B start: halo row of this K step + tap shift (+ parity plane for stride 2); D column block
+          const uint32_t ak = abase + tap_boff[m];
+          const uint64_t ah = a_t | (uint64_t)(ak >> 4), al = a_t | (uint64_t)((ak + a_lo) >> 4);
+          const uint32_t dcol = tmem + tap_col[m];
+          if (elect_one()) {
+            umma_bf16(dcol, dyh, ah, idesc, acc);
+            umma_bf16(dcol, dyh, al, idesc, 1u);
+            umma_bf16(dcol, dyl, ah, idesc, 1u);
+          }
+        }
+      }
+      if (elect_one()) umma_commit(BAR(4 + s));
+    }
+    if (elect_one()) umma_commit(BAR(8));
+  } else if (warp < W_EPI) {
+    // ===== transform teams: team k stages tiles k, k+nstage, ... into stage k =====
+    const int TS = NTRANS / g.nstage;
+    const int team = threadIdx.x / TS, t = threadIdx.x - team * TS;
+    for (int it = team; it < ntiles; it += g.nstage) {
+      const int s = team;
+      mbar_wait(BAR(4 + s), (uint32_t)(((it / g.nstage) & 1) ^ 1));
+      const long tile0 = (t_beg + it) * TILE;
+      int* tab = s_tab + s * tab_stride;
+      int* dtab = tab + g.Lpad * g.nq;
+      for (int pos = t; pos < g.Lpad; pos += TS) {
+        int s0, s1, s2, s3, d;
+        virt_decode((pos < g.L) ? tile0 - g.center + pos : -1, p, s0, s1, s2, s3, d);
+        if (g.nq == 1) tab[pos] = s0;
+        else { tab[pos * 4 + 0] = s0; tab[pos * 4 + 1] = s1; tab[pos * 4 + 2] = s2; tab[pos * 4 + 3] = s3; }
+        const int m = pos - g.center;
+        if (m >= 0 && m < TILE) dtab[m] = d;
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TS) : "memory");
+      uint8_t* st = Sbase + (size_t)s * g.stage_bytes;
+      // dy tile: channels [co_lo, co_lo + co_n)
+      if (g.Vd == 4) stage_rows<4>(p.dy, p.Cout, co_lo, co_n, TILE, dtab, 1, 0, st, d_lo, (uint32_t)g.d_plane, SWd, 0, nullptr, nullptr, false, 0, t, TS);
+      else stage_rows<2>(p.dy, p.Cout, co_lo, co_n, TILE, dtab, 1, 0, st, d_lo, (uint32_t)g.d_plane, SWd, 0, nullptr, nullptr, false, 0, t, TS);
+      // T(x) halo: channels [ci_lo, ci_lo + ci_n) of each parity plane
+      for (int q = 0; q < g.nq; ++q) {
+        if (g.Va == 4) stage_rows<4>(p.x, p.Cin, ci_lo, ci_n, g.Lpad, tab, g.nq, q, st + a_off, a_lo, (uint32_t)g.a_plane, SWa,
+                                     (uint32_t)(q * g.CI * 2), s_sc, s_sh, p.in_scale != nullptr, p.in_relu, t, TS);
+        else stage_rows<2>(p.x, p.Cin, ci_lo, ci_n, g.Lpad, tab, g.nq, q, st + a_off, a_lo, (uint32_t)g.a_plane, SWa,
+                           (uint32_t)(q * g.CI * 2), s_sc, s_sh, p.in_scale != nullptr, p.in_relu, t, TS);
+      }
+      fence_proxy_async();
+      mbar_arrive(BAR(s));
+    }
+  } else {
+    // ===== epilogue warps: D[co][tap*CI + ci] -> dw (fp32 atomics) =====
+    mbar_wait(BAR(8), 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int co = co_lo + q * 32 + lane;
+    const bool rowok = (q * 32 + lane) < co_n && ntiles > 0;
+    for (int tap = 0; tap < g.taps; ++tap) {
+      for (int c0 = 0; c0 < g.CI; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * g.CI + c0), v);
+        if (rowok) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int ci = ci_lo + c0 + i;
+            if (c0 + i < ci_n) atomicAdd(p.dw + ((long)co * p.lddw + ci) * g.taps + tap, v[i]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem, g.tmem_cols);
+}
+
+}  // namespace
+
+extern "C" {
+
+int hcm_tc_wgrad_supported(int B, int H, int W, int Cin, int Cout, int ks, int stride) {
+  if (!((ks == 3 && (stride == 1 || stride == 2)) || (ks == 1 && stride == 1))) return 0;
+  WGeo g = make_wgeo(B, H, W, Cin, Cout, ks, stride);
+  return wgeo_ok(g, H, W, Cin, Cout, ks, stride) ? 1 : 0;
+}
+
+// dw[Cout,Cin,ks,ks] += sum_pixels dy * T(x)   (fp32 atomics across CTAs; the caller zeroes dw once per step).
+// lddw > 0: dw is a column block of a wider [Cout][lddw][ks][ks] tensor
+int hcm_tc_wgrad(const float* x, const float* dy, float* dw, int lddw, int B, int H, int W, int Cin, int Cout, int ks, int stride,
+                 const float* in_scale, const float* in_shift, int in_relu, cudaStream_t stream) {
+  HCM_CHECK_ARG(x && dy && dw, "tc_wgrad: null pointer");
+  HCM_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "tc_wgrad: in_scale/in_shift must come together");
+  WParams p;
+  p.g = make_wgeo(B, H, W, Cin, Cout, ks, stride);
+  HCM_CHECK_ARG(wgeo_ok(p.g, H, W, Cin, Cout, ks, stride), "tc_wgrad: unsupported geometry (Cin=%d Cout=%d ks=%d stride=%d)", Cin,
+                Cout, ks, stride);
+  p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.in_relu = in_relu; p.dy = dy; p.dw = dw;
+  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.lddw = lddw > 0 ? lddw : Cin;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { hcm_set_error("tc_wgrad: smem attribute: %s", cudaGetErrorString(e)); return HCM_ERR_CUDA; }
+    configured = true;
+  }
+  dim3 grid(p.g.ntr, p.g.nsplit, p.g.nblk);
+  tc_wgrad2_kernel<<<grid, NTHREADS_W, p.g.smem, stream>>>(p);
+  HCM_LAUNCH_CHECK("tc_wgrad");
+  return HCM_OK;
+}
+
+}  // extern "C"

@@ -299,7 +299,7 @@ class Engine:
                 spec["g_out"], spec["g_acc"], P, cout)
             dy = spec["dy"]
             if self.use_tc and K.tc_wgrad_supported(B, H, W, cin, cout, ks, stride):
-                p.b(K.tc_wgrad, x.data, dy, st.grad(ck + ".weight"), 0, B, H, W, cin, cout, ks, x.scale, x.shift, int(x.relu))
+                p.b(K.tc_wgrad, x.data, dy, st.grad(ck + ".weight"), 0, B, H, W, cin, cout, ks, stride, x.scale, x.shift, int(x.relu))
             else:
                 p.b(K.conv2d_wgrad, x.data, dy, st.grad(ck + ".weight"), B, H, W, cin, cout, ks, stride, x.scale, x.shift,
                     int(x.relu))
@@ -642,7 +642,7 @@ class Engine:
                 else:
                     Gj = K.empty(B, ft.H, ft.W, 128)
                     p.b(K.upsample_adjoint, G, Gj, 0, B, h, h, 128, j)
-                p.b(K.tc_wgrad, ft.data, Gj, gs[j], cm, B, ft.H, ft.W, ft.C, 128, 1, None, None, 0)
+                p.b(K.tc_wgrad, ft.data, Gj, gs[j], cm, B, ft.H, ft.W, ft.C, 128, 1, 1, None, None, 0)
                 gx, acc = p.grad(ft)
                 wpt = K.empty((K.tc_conv_wpack_bytes(B, ft.H, ft.W, 128, ft.C, 1) + 3) // 4)
                 p.b(K.tc_conv_pack, ws[j], cm, wpt, B, ft.H, ft.W, 128, ft.C, 1, 1)

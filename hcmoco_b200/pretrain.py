@@ -144,10 +144,10 @@ class PretrainStep:
                 n = getattr(fn, "__name__", "fn")
                 n = {"fwd_logits": "nce_logits", "bwd": "nce_bwd"}.get(n, n[4:] if n.startswith("hcm_") else n)
                 names.append(n)
-                o = {"tc_conv": 4, "conv2d_fwd": 4, "conv2d_dgrad": 3, "conv2d_wgrad": 3, "tc_wgrad": 3}.get(n)
+                o = {"tc_conv": 4, "conv2d_fwd": 4, "conv2d_dgrad": 3, "conv2d_wgrad": 3, "tc_wgrad": 4, "tc_dgrad_s2": 3}.get(n)
                 shapes.append(None if o is None else "%s %dx%d %d->%d k%d%s" % (
                     n, args[o + 1], args[o + 2], args[o + 3], args[o + 4], args[o + 5],
-                    "" if n.startswith("tc_") else " s%d" % args[o + 6]))
+                    "" if n == "tc_dgrad_s2" else " s%d" % args[o + 6]))
 
         go(e.plan.fwd)
         e.K.zero(e.store.g, e.store.n * 4)

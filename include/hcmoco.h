@@ -68,10 +68,10 @@ int hcm_tc_dgrad_s2_pack(const float* w, void* wpack, int B, int H, int W, int C
 int hcm_tc_dgrad_s2(const float* dy, const void* wpack, float* dx, int B, int H, int W, int Cin, int Cout, int accumulate,
                     cudaStream_t stream);
 
-/* tensor-core weight gradient (tc_wgrad.cu): dw[Cout,Cin,ks,ks] += sum_pixels dy * T(x), stride 1 */
+/* tensor-core weight gradient (tc_wgrad2.cu): dw[Cout,Cin,ks,ks] += sum_pixels dy * T(x); 3x3 stride 1|2, 1x1 */
 int hcm_tc_wgrad_supported(int B, int H, int W, int Cin, int Cout, int ks, int stride);
 int hcm_tc_wgrad(const float* x, const float* dy, float* dw, int lddw, int B, int H, int W, int Cin, int Cout, int ks,
-                 const float* in_scale, const float* in_shift, int in_relu, cudaStream_t stream);
+                 int stride, const float* in_scale, const float* in_shift, int in_relu, cudaStream_t stream);
 
 /* ---- train-mode batch norm (bn.cu) : nn.BatchNorm2d(momentum=0.01) official_hrnet.py:22-23 (+ReLU /
  *      residual add :44-60, :86-101) and nn.BatchNorm1d networks/SGCN/sem_gcn.py:13 ---- */

@@ -21,14 +21,14 @@ K.tc_conv_pack(w, 0, wp, B, H, W, Cin, Cout, ks, 0)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 for i in range(reps):
     K.tc_conv(x, wp, None, y, B, H, W, Cin, Cout, ks, 1, sc, sh, 1, 0)
-    K.tc_wgrad(x, dy, dw, 0, B, H, W, Cin, Cout, ks, sc, sh, 1)
+    K.tc_wgrad(x, dy, dw, 0, B, H, W, Cin, Cout, ks, 1, sc, sh, 1)
 torch.cuda.synchronize()
 ev[0].record()
 for i in range(20):
     K.tc_conv(x, wp, None, y, B, H, W, Cin, Cout, ks, 1, sc, sh, 1, 0)
 ev[1].record()
 for i in range(20):
-    K.tc_wgrad(x, dy, dw, 0, B, H, W, Cin, Cout, ks, sc, sh, 1)
+    K.tc_wgrad(x, dy, dw, 0, B, H, W, Cin, Cout, ks, 1, sc, sh, 1)
 ev[2].record()
 torch.cuda.synchronize()
 fl = 2.0 * B * H * W * Cin * Cout * ks * ks

@@ -145,12 +145,12 @@ class TorchKernels:
         return self.conv2d_dgrad(dy, w, dx, B, H, W, Cin, Cout, 3, 2, accumulate)
 
     def tc_wgrad_supported(self, B, H, W, Cin, Cout, ks, stride):
-        return int(stride == 1 and self.tc_conv_supported(B, H, W, Cin, Cout, ks, stride))
+        return self.tc_conv_supported(B, H, W, Cin, Cout, ks, stride)
 
-    def tc_wgrad(self, x, dy, dw, lddw, B, H, W, Cin, Cout, ks, sc, sh, relu):
+    def tc_wgrad(self, x, dy, dw, lddw, B, H, W, Cin, Cout, ks, stride, sc, sh, relu):
         ld = lddw if lddw > 0 else Cin
         tmp = torch.zeros(Cout, Cin, ks, ks, dtype=dw.dtype, device=dw.device)
-        self.conv2d_wgrad(x, dy, tmp, B, H, W, Cin, Cout, ks, 1, sc, sh, relu)
+        self.conv2d_wgrad(x, dy, tmp, B, H, W, Cin, Cout, ks, stride, sc, sh, relu)
         torch.as_strided(dw, (Cout, Cin, ks, ks), (ld * ks * ks, ks * ks, ks, 1), dw.storage_offset()).add_(tmp)
         return 0
 

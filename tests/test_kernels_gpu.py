@@ -363,10 +363,10 @@ def test_tc_wgrad(KK, shape):
     sc, sh = rnd(Cin, seed=1).abs() + 0.5, rnd(Cin, seed=2)
     dw1 = rnd(Cout, Cin, ks, ks, seed=6)
     dw2 = dw1.clone()
-    kc.tc_wgrad(x, dy, dw1, 0, B, H, W, Cin, Cout, ks, sc, sh, 1)
+    kc.tc_wgrad(x, dy, dw1, 0, B, H, W, Cin, Cout, ks, 1, sc, sh, 1)
     kr.conv2d_wgrad(x, dy, dw2, B, H, W, Cin, Cout, ks, 1, sc, sh, 1)
     assert rel(dw1, dw2) < 3e-5, rel(dw1, dw2)
-    kc.tc_wgrad(x, dy, dw1, 0, B, H, W, Cin, Cout, ks, None, None, 0)
+    kc.tc_wgrad(x, dy, dw1, 0, B, H, W, Cin, Cout, ks, 1, None, None, 0)
     kr.conv2d_wgrad(x, dy, dw2, B, H, W, Cin, Cout, ks, 1, None, None, 0)
     assert rel(dw1, dw2) < 3e-5, rel(dw1, dw2)
 
@@ -409,3 +409,17 @@ def test_tc_dgrad_stride2(KK, shape):
         kc.tc_dgrad_s2(dy, wp, dx1, B, H, W, Cin, Cout, acc)
         kr.conv2d_dgrad(dy, w, dx2, B, H, W, Cin, Cout, 3, 2, acc)
         assert rel(dx1, dx2) < 3e-5, (acc, rel(dx1, dx2))
+
+
+@pytest.mark.parametrize("shape", TC_S2)
+def test_tc_wgrad_stride2(KK, shape):
+    B, H, W, Cin, Cout = shape
+    kc, kr = KK
+    assert kc.tc_wgrad_supported(B, H, W, Cin, Cout, 3, 2)
+    x, dy = rnd(B, H, W, Cin), rnd(B, H // 2, W // 2, Cout, seed=3)
+    sc, sh = rnd(Cin, seed=1).abs() + 0.5, rnd(Cin, seed=2)
+    dw1 = rnd(Cout, Cin, 3, 3, seed=6)
+    dw2 = dw1.clone()
+    kc.tc_wgrad(x, dy, dw1, 0, B, H, W, Cin, Cout, 3, 2, sc, sh, 1)
+    kr.conv2d_wgrad(x, dy, dw2, B, H, W, Cin, Cout, 3, 2, sc, sh, 1)
+    assert rel(dw1, dw2) < 3e-5, rel(dw1, dw2)
