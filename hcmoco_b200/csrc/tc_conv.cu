@@ -622,6 +622,53 @@ __global__ void tc_pack_dgrad2_kernel(const float* __restrict__ w, uint8_t* __re
   }
 }
 
+// All weight packs of a step in ONE launch (the weights only change at the optimiser step): blockIdx.x = global K-step index,
+// jobs[j] = {w, out, Cin, Cout, ks, mode (0 forward, 1 transposed stride-1 dgrad, 2 stride-2 dgrad), ldw, first_step}
+struct PackJob { long long w, out, Cin, Cout, ks, mode, ldw, first; };
+__global__ void tc_pack_batch_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  __shared__ PackJob jb;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = njobs - 1;                                   // last job with first <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].first <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    jb = jobs[lo];
+  }
+  __syncthreads();
+  const float* w = reinterpret_cast<const float*>(jb.w);
+  const int Cin = (int)jb.Cin, Cout = (int)jb.Cout, ks = (int)jb.ks, mode = (int)jb.mode;
+  const int step = (int)((long long)blockIdx.x - jb.first);
+  int Npad, Cin16, taps, Cp = 0;
+  if (mode == 2) { Cp = ceil_to(Cin, 16); Npad = 4 * Cp; Cin16 = ceil_to(Cout, 16); taps = 4; }   // (Cin, Cout) of the conv weight
+  else { Npad = ceil_to(Cout, 16); Cin16 = ceil_to(Cin, 16); taps = ks * ks; }
+  const int nj = Cin16 / 16;
+  const int tap = step / nj, j = step - tap * nj;
+  uint8_t* slab = reinterpret_cast<uint8_t*>(jb.out) + (size_t)step * 64 * Npad;
+  const int wCin = jb.ldw > 0 ? (int)jb.ldw : (mode == 1 ? Cout : Cin);
+  for (int e = threadIdx.x; e < Npad * 16; e += blockDim.x) {
+    const int n = e >> 4, k = e & 15;
+    float v = 0.f;
+    if (mode == 2) {
+      const int du = tap >> 1, dv = tap & 1;
+      const int q = n / Cp, ci = n - q * Cp;
+      const int py = q >> 1, px = q & 1;
+      const int r = (py == 0) ? (du == 0 ? 1 : -1) : (du == 0 ? 2 : 0);
+      const int sx = (px == 0) ? (dv == 0 ? 1 : -1) : (dv == 0 ? 2 : 0);
+      const int co = 16 * j + k;
+      if (r >= 0 && sx >= 0 && ci < Cin && co < Cout) v = w[(((long)co * Cin + ci) * 3 + r) * 3 + sx];
+    } else {
+      const int c = 16 * j + k;
+      if (n < Cout && c < Cin) v = mode == 1 ? w[((long)c * wCin + n) * taps + (taps - 1 - tap)] : w[((long)n * wCin + c) * taps + tap];
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const size_t chunk = (size_t)(k >> 3) * (2 * Npad) * 16;
+    *reinterpret_cast<__nv_bfloat16*>(slab + chunk + (size_t)n * 16 + (k & 7) * 2) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(slab + chunk + (size_t)(Npad + n) * 16 + (k & 7) * 2) = lo;
+  }
+}
+
 bool dgrad2_ok(const Geo& g, int H, int W, int Cin, int Cout) {
   return ((H | W) & 1) == 0 && (Cin % 2) == 0 && (Cout % 2) == 0 && Cout <= 256 && g.Npad <= 256 && g.ngroups <= MAXG &&
          g.Lpad <= MAX_LPAD && g.Mv < (1L << 31) && (g.w_resident || g.wst >= 2) && g.smem <= 227 * 1024 &&
@@ -690,6 +737,16 @@ int hcm_tc_dgrad_s2(const float* dy, const void* wpack, float* dx, int B, int H,
   p.wpack = reinterpret_cast<const uint8_t*>(wpack); p.bias = nullptr; p.y = dx; p.accumulate = accumulate;
   p.B = B; p.H = H; p.W = W; p.Cin = Cout; p.Cout = Cin;   // as seen by the GEMM: staged channels = Cout(w), output channels = Cin(w)
   return launch_tc(p, stream, "tc_dgrad_s2");
+}
+
+// One launch for all weight packs of a step.  jobs (device): njobs x 8 int64 {w ptr, out ptr, Cin, Cout, ks, mode, ldw, first_step}
+// with mode 0 = hcm_tc_conv_pack(transpose 0), 1 = (transpose 1), 2 = hcm_tc_dgrad_s2_pack; (Cin, Cout) as passed to those calls;
+// first_step = running sum of the jobs' K-step counts (ks*ks*ceil16(Cin)/16, mode 2: 4*ceil16(Cout)/16); total_steps = their sum.
+int hcm_tc_pack_batch(const long long* jobs, int njobs, int total_steps, cudaStream_t stream) {
+  HCM_CHECK_ARG(jobs && njobs >= 1 && total_steps >= 1, "tc_pack_batch: bad args");
+  tc_pack_batch_kernel<<<total_steps, 128, 0, stream>>>(reinterpret_cast<const PackJob*>(jobs), njobs);
+  HCM_LAUNCH_CHECK("tc_pack_batch");
+  return HCM_OK;
 }
 
 // 1 if hcm_tc_conv can run this convolution: 3x3 stride 1/2 (even H,W for stride 2) or 1x1 stride 1, even channels <= 256

@@ -209,6 +209,8 @@ class Engine:
     def build(self):
         K, B, R, J = self.K, self.B, self.R, self.J
         self.plan = p = Plan(K)
+        self.pack_jobs = []
+        p.f(self._run_packs)
         maxc = 4 * max(self.ch[-1], 256)
         # shared scratch (single stream => sequential reuse is safe)
         self.part = K.empty(2 * 4096 * 2 * 256)
@@ -249,8 +251,38 @@ class Engine:
         if self.stage == 2:
             self._stage2_losses()
         self.n_loss_bwd = p.finish(n_model_builders)      # bwd[:n_loss_bwd] = loss kernels, the rest = model backward
+        self._finish_packs()
         self.built = True
         return self
+
+    # ---- weight packing for the tensor-core kernels: every job of the step goes into ONE launch at the head of the forward
+    def _pack_job(self, w, ldw, wp, geo, cin, cout, ks, mode):
+        self.pack_jobs.append((w, ldw, wp, geo, cin, cout, ks, mode))
+
+    def _run_packs(self):
+        K = self.K
+        if not self.pack_jobs:
+            return
+        if hasattr(K, "tc_pack_batch") and self.pack_table is not None:
+            K.tc_pack_batch(self.pack_table, len(self.pack_jobs), self.pack_steps)
+            return
+        for w, ldw, wp, (B, H, W), cin, cout, ks, mode in self.pack_jobs:
+            if mode == 2:
+                K.tc_dgrad_s2_pack(w, wp, B, H, W, cin, cout)
+            else:
+                K.tc_conv_pack(w, ldw, wp, B, H, W, cin, cout, ks, mode)
+
+    def _finish_packs(self):
+        self.pack_table, self.pack_steps = None, 0
+        if not self.pack_jobs or not hasattr(self.K, "tc_pack_batch"):
+            return
+        rows, first = [], 0
+        for w, ldw, wp, geo, cin, cout, ks, mode in self.pack_jobs:
+            rows.append([w.data_ptr(), wp.data_ptr(), cin, cout, ks, mode, ldw, first])
+            kch = (cout if mode == 2 else cin)
+            first += (4 if mode == 2 else ks * ks) * ((kch + 15) // 16)
+        self.pack_steps = first
+        self.pack_table = torch.tensor(rows, dtype=torch.int64).to(self.K.device)
 
     # ---- conv + train-mode BN; output is lazy (raw conv output + per-channel affine)
     def _conv_bn(self, x, ck, bk, stride, relu):
@@ -271,7 +303,7 @@ class Engine:
             nb = K.tc_conv_wpack_bytes(B, H, W, cin, cout, ks)
             wp_f = K.empty((nb + 3) // 4)
             rows = K.colstat_rows(P, cout)
-            p.f(K.tc_conv_pack, w, 0, wp_f, B, H, W, cin, cout, ks, 0)
+            self._pack_job(w, 0, wp_f, (B, H, W), cin, cout, ks, 0)
             p.f(K.tc_conv, x.data, wp_f, None, y, B, H, W, cin, cout, ks, stride, x.scale, x.shift, int(x.relu), 0)
             p.f(K.bn_stats, y, P, cout, self.part)
         else:
@@ -314,11 +346,11 @@ class Engine:
                     # data gradient = the same tensor-core conv run on dy with transposed + flipped weights
                     nbt = K.tc_conv_wpack_bytes(B, H, W, cout, cin, ks)
                     wp_t = K.empty((nbt + 3) // 4)
-                    p.b(K.tc_conv_pack, w, 0, wp_t, B, H, W, cout, cin, ks, 1)
+                    self._pack_job(w, 0, wp_t, (B, H, W), cout, cin, ks, 1)
                     p.b(K.tc_conv, dy, wp_t, None, gx, B, H, W, cout, cin, ks, 1, None, None, 0, acc)
                 elif tc and stride == 2 and ks == 3 and K.tc_dgrad_s2_supported(B, H, W, cin, cout):
                     wp_t = K.empty((K.tc_dgrad_s2_wpack_bytes(B, H, W, cin, cout) + 3) // 4)
-                    p.b(K.tc_dgrad_s2_pack, w, wp_t, B, H, W, cin, cout)
+                    self._pack_job(w, 0, wp_t, (B, H, W), cin, cout, 3, 2)
                     p.b(K.tc_dgrad_s2, dy, wp_t, gx, B, H, W, cin, cout, acc)
                 else:
                     p.b(K.conv2d_dgrad, dy, w, gx, B, H, W, cin, cout, ks, stride, acc)
@@ -622,7 +654,7 @@ class Engine:
             if not K.tc_conv_supported(B, ft.H, ft.W, ft.C, 128, 1, 1):
                 raise NotImplementedError("1x1 projection: unsupported geometry")
             wp = K.empty((K.tc_conv_wpack_bytes(B, ft.H, ft.W, ft.C, 128, 1) + 3) // 4)
-            p.f(K.tc_conv_pack, ws[j], cm, wp, B, ft.H, ft.W, ft.C, 128, 1, 0)
+            self._pack_job(ws[j], cm, wp, (B, ft.H, ft.W), ft.C, 128, 1, 0)
             p.f(K.tc_conv, ft.data, wp, None, y, B, ft.H, ft.W, ft.C, 128, 1, 1, None, None, 0, 0)
             ys.append(y)
         out = Act(K.empty(B, h, h, 128), B, h, h, 128)
@@ -645,7 +677,7 @@ class Engine:
                 p.b(K.tc_wgrad, ft.data, Gj, gs[j], cm, B, ft.H, ft.W, ft.C, 128, 1, 1, None, None, 0)
                 gx, acc = p.grad(ft)
                 wpt = K.empty((K.tc_conv_wpack_bytes(B, ft.H, ft.W, 128, ft.C, 1) + 3) // 4)
-                p.b(K.tc_conv_pack, ws[j], cm, wpt, B, ft.H, ft.W, 128, ft.C, 1, 1)
+                self._pack_job(ws[j], cm, wpt, (B, ft.H, ft.W), 128, ft.C, 1, 1)
                 p.b(K.tc_conv, Gj, wpt, None, gx, B, ft.H, ft.W, 128, ft.C, 1, 1, None, None, 0, acc)
 
         p.on_backward(backward)

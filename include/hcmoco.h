@@ -55,6 +55,9 @@ long hcm_tc_conv_wpack_bytes(int B, int H, int W, int Cin, int Cout, int ks);
  * of a wider [O][ldw][ks][ks] tensor (per-branch blocks of the 1x1 projection); lddw likewise for hcm_tc_wgrad */
 int hcm_tc_conv_pack(const float* w, int ldw, void* wpack, int B, int H, int W, int Cin, int Cout, int ks, int transpose,
                      cudaStream_t stream);
+/* all weight packs of a step in one launch: jobs (device) = njobs x 8 int64 {w ptr, out ptr, Cin, Cout, ks, mode, ldw, first_step};
+ * mode 0/1 = hcm_tc_conv_pack(transpose 0/1), 2 = hcm_tc_dgrad_s2_pack, (Cin, Cout) as passed to those calls */
+int hcm_tc_pack_batch(const long long* jobs, int njobs, int total_steps, cudaStream_t stream);
 /* y[B,Ho,Wo,Cout] (+)= conv(T(x[B,H,W,Cin])) (+bias), 3x3 stride 1|2 or 1x1, pad (ks-1)/2 */
 int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, int B, int H, int W, int Cin, int Cout,
                 int ks, int stride, const float* in_scale, const float* in_shift, int in_relu, int accumulate,
