@@ -121,32 +121,52 @@ class ParamStore:
         return OrderedDict((k, self.export(self.g, k)) for k in self.keys if not L.is_buffer(k))
 
 
+FORK, JOIN = "fork", "join"      # program markers: the side stream starts from / is merged back into the main stream
+
+
 class Plan:
     """Recorded launch lists.  `f` appends a forward launch; ops register a backward *builder* that is
     invoked in reverse op order by `finish()`, so that first-writer / accumulate flags of gradient
-    buffers are resolved statically."""
+    buffers are resolved statically.
+
+    Every launch carries a stream tag (0 = main, 1 = side): the two HRNet encoders are independent between the input
+    split and the heads, so encoder2's launches go to a side stream (forked / joined with events, captured into the
+    same CUDA graph); its small-grid and elementwise kernels then fill the SMs the other encoder's kernels leave idle."""
 
     def __init__(self, K):
         self.K = K
         self.fwd, self.bwd, self._builders = [], [], []
-        self._cur = self.fwd
+        self.tag = 0
+        self.side = None
+        self._bwd_forked = False
 
     def f(self, fn, *args):
-        self.fwd.append((fn, args))
+        self.fwd.append((fn, args, self.tag))
 
     def b(self, fn, *args):
-        self.bwd.append((fn, args))
+        if self.tag == 1 and not self._bwd_forked:
+            self.bwd.append((FORK, (), 0))
+            self._bwd_forked = True
+        self.bwd.append((fn, args, self.tag))
+
+    def mark_f(self, what):
+        self.fwd.append((what, (), 0))
 
     def on_backward(self, builder):
-        self._builders.append(builder)
+        self._builders.append((builder, self.tag))
 
     def finish(self, mark=0):
         """Run the builders in reverse registration order; returns len(bwd) after the builders >= `mark` ran."""
-        for bld in reversed(self._builders[mark:]):
+        for bld, tag in reversed(self._builders[mark:]):
+            self.tag = tag
             bld()
         n = len(self.bwd)
-        for bld in reversed(self._builders[:mark]):
+        for bld, tag in reversed(self._builders[:mark]):
+            self.tag = tag
             bld()
+        self.tag = 0
+        if self._bwd_forked:
+            self.bwd.append((JOIN, (), 0))
         self._builders = []
         return n
 
@@ -167,16 +187,44 @@ class Plan:
             act.grad_ready = True
         return act.grad
 
-    @staticmethod
-    def run(prog):
-        for fn, args in prog:
-            fn(*args)
+    def run(self, prog, two_streams=True):
+        """Enqueue a program.  With a CUDA device and two_streams, tag-1 launches between FORK and JOIN go to the side stream."""
+        use_side = two_streams and self.K.device == "cuda" and any(e[0] == FORK for e in prog)
+        if not use_side:
+            for fn, args, _ in prog:
+                if fn is not FORK and fn is not JOIN:
+                    fn(*args)
+            return
+        if self.side is None:
+            self.side = torch.cuda.Stream()
+        main, side, forked = torch.cuda.current_stream(), self.side, False
+        for fn, args, tag in prog:
+            if fn is FORK:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                forked = True
+            elif fn is JOIN:
+                if forked:
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    main.wait_event(ev)
+                    forked = False
+            elif tag == 1 and forked:
+                with torch.cuda.stream(side):
+                    fn(*args)
+            else:
+                fn(*args)
+        if forked:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)
 
 
 class Engine:
     def __init__(self, K, width=18, stage=1, skeleton="mpii", B=2, R=224, n_data=20000, nce_k=16384, nce_t=0.07,
                  nce_m=0.5, temperature=0.07, num_samples=400, feat_dim=128, world_size=1, train=True, use_tc=True,
-                 store=None):
+                 store=None, two_streams=True):
         assert feat_dim == 128, "the NCE / loss kernels are specialised for feat_dim=128"
         assert R % 32 == 0, "HRNet needs the input side to be a multiple of 32"
         assert B >= 2, "the reference collapses B=1 (mem_bank.py:39 out.squeeze())"
@@ -187,6 +235,7 @@ class Engine:
         self.n_data, self.K1, self.T_nce, self.m_nce = n_data, nce_k + 1, nce_t, nce_m
         self.T, self.S = temperature, num_samples
         self.world = world_size
+        self.two_streams = two_streams   # encoder2 on a side stream (see Plan)
         self.use_tc = use_tc     # tensor-core path for the stride-1 convs (SIMT fp32 implicit GEMM otherwise)
         self.ch = L.WIDTHS[width]
         self.cm = sum(self.ch)
@@ -213,8 +262,9 @@ class Engine:
         p.f(self._run_packs)
         maxc = 4 * max(self.ch[-1], 256)
         # shared scratch (single stream => sequential reuse is safe)
-        self.part = K.empty(2 * 4096 * 2 * 256)
-        self.k1, self.k2, self.k3 = K.empty(maxc), K.empty(maxc), K.empty(maxc)
+        # scratch per stream tag (launches with the same tag are sequential, so reuse within a tag is safe)
+        self._part = [K.empty(2 * 4096 * 2 * 256) for _ in range(2)]
+        self._k = [(K.empty(maxc), K.empty(maxc), K.empty(maxc)) for _ in range(2)]
         # step inputs (static buffers; the caller copies each batch in)
         self.x = K.zeros(B, 6, R, R)
         self.skel = K.zeros(B, J, 2)
@@ -231,8 +281,12 @@ class Engine:
             xin = K.empty(B, R, R, 3)
             p.f(K.nchw_to_nhwc, self.x, xin, B, 6, R * R, 3 * m, 3)
             xs.append(Act(xin, B, R, R, 3, needs_grad=False))
+        p.mark_f(FORK)
         self.feat1 = self._hrnet("encoder1.", xs[0])
+        p.tag = 1
         self.feat2 = self._hrnet("encoder2.", xs[1])
+        p.tag = 0
+        p.mark_f(JOIN)
         self.feat3 = self._sgcn("encoder3.", self.skel)
         self.f = K.empty(B, 384)
         self.df = K.zeros(B, 384)
@@ -254,6 +308,22 @@ class Engine:
         self._finish_packs()
         self.built = True
         return self
+
+    @property
+    def part(self):
+        return self._part[self.plan.tag]
+
+    @property
+    def k1(self):
+        return self._k[self.plan.tag][0]
+
+    @property
+    def k2(self):
+        return self._k[self.plan.tag][1]
+
+    @property
+    def k3(self):
+        return self._k[self.plan.tag][2]
 
     # ---- weight packing for the tensor-core kernels: every job of the step goes into ONE launch at the head of the forward
     def _pack_job(self, w, ldw, wp, geo, cin, cout, ks, mode):
@@ -806,15 +876,15 @@ class Engine:
             self.dense_idx.copy_(dense_idx, non_blocking=True)
 
     def forward(self):
-        Plan.run(self.plan.fwd)
+        self.plan.run(self.plan.fwd, self.two_streams)
 
     def backward(self):
         self.K.zero(self.store.g, self.store.n * self.store.g.element_size())
-        Plan.run(self.plan.bwd)
+        self.plan.run(self.plan.bwd, self.two_streams)
 
     # ---- model-only programs for the autograd bridge (api.HCMoCoModel): the caller owns the losses
     def forward_model(self):
-        Plan.run(self.plan.fwd[:self.n_model_fwd])
+        self.plan.run(self.plan.fwd[:self.n_model_fwd], self.two_streams)
 
     def seed_output_grads(self, gf, g_feat3=None, g_lm1=None, g_lm2=None):
         """Write d(loss)/d(outputs) into the buffers the model-backward program starts from."""
@@ -836,7 +906,7 @@ class Engine:
 
     def backward_model(self):
         self.K.zero(self.store.g, self.store.n * self.store.g.element_size())
-        Plan.run(self.plan.bwd[self.n_loss_bwd:])
+        self.plan.run(self.plan.bwd[self.n_loss_bwd:], self.two_streams)
 
     def draw_dense(self, injected=None):
         """Dense pixel samples: S draws with replacement from each sample's nearest-resized depth mask

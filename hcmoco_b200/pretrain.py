@@ -135,7 +135,9 @@ class PretrainStep:
         ev, names, shapes = [], [], []
 
         def go(prog):
-            for fn, args in prog:
+            for fn, args, _tag in prog:
+                if isinstance(fn, str):          # FORK / JOIN markers
+                    continue
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 fn(*args)
