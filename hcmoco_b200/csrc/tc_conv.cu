@@ -28,7 +28,7 @@ constexpr int NTRANS = 512;                  // transform threads: warps 0..15 (
 constexpr int NTHREADS = NTRANS + 128 + 64;  // then 4 epilogue warps, the TMA producer warp, and last the MMA issuer + TMEM owner
 // (the SMSP arbiter favours the highest warp id: the single MMA-issuing warp must not starve behind busy transform warps)
 constexpr int W_EPI = NTRANS / 32, W_TMA = W_EPI + 4, W_MMA = W_TMA + 1;
-constexpr int MAXG = 8;
+constexpr int MAXG = 16;
 constexpr int MAX_LPAD = 512;
 constexpr int HDR_BYTES = 4096 + 4096;      // barriers / tmem ptr / scale / shift | 4 per-team unit tables; the per-stage source tables follow
 constexpr int MAX_ASTAGE = 4;
@@ -38,6 +38,7 @@ constexpr int MAX_STEPS = 144;                // 9 taps x 256/16 channels
 struct Geo {
   int mode;          // 0: convolution; 1: data gradient of a 3x3 stride-2 convolution (see hcm_tc_dgrad_s2)
   int Cp;            // mode 1: padded original Cin = width of one output parity block
+  int nqs;           // mode 1: output parities handled per launch (4, 2 or 1 so that N = nqs*Cp <= 256)
   int stride, ks, taps, nq, Hp, Wp, Ho, Wo, center, L, Lpad, Npad, Cin16, SC, SW, KB, cg, ngroups, nblk, nsteps;
   int concat, acc_cols, acc_stages, tmem_cols, nastage, w_resident, wst, spb, grid, V;
   long Mv, tiles;
@@ -46,7 +47,7 @@ struct Geo {
 
 Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride, int mode = 0) {
   Geo g;
-  g.mode = mode; g.Cp = 0;
+  g.mode = mode; g.Cp = 0; g.nqs = 0;
   g.stride = stride; g.ks = ks; g.taps = ks * ks;
   g.nq = (stride == 2) ? 4 : 1;
   g.Ho = (stride == 2) ? H / 2 : H;
@@ -60,11 +61,12 @@ Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride, int mod
     g.Ho = H / 2; g.Wo = W / 2;
     g.Hp = g.Ho + 1; g.Wp = g.Wo + 1; g.center = 0; g.L = TILE_M + g.Wp + 1;
     g.Cp = ceil_to(Cout, 16);
+    g.nqs = (4 * g.Cp <= 256) ? 4 : ((2 * g.Cp <= 256) ? 2 : 1);
   }
   g.Mv = (long)B * g.Hp * g.Wp;
   g.tiles = (g.Mv + TILE_M - 1) / TILE_M;
   g.Lpad = ceil_to(g.L, 16);
-  g.Npad = (mode == 1) ? 4 * g.Cp : ceil_to(Cout, 16);
+  g.Npad = (mode == 1) ? g.nqs * g.Cp : ceil_to(Cout, 16);
   g.Cin16 = ceil_to(Cin, 16);
   g.SC = g.nq * g.Cin16;                      // staged channels per position
   g.V = (Cin % 4 == 0) ? 4 : 2;
@@ -137,6 +139,7 @@ struct TcParams {
   float* y;
   int accumulate;
   int B, H, W, Cin, Cout;
+  int q0;                      // mode 1: first output parity of this launch
   long long* dbg;
   Geo g;
   // host-built issue schedule: steps ordered (group, tap, K16 step); x = byte offset of the A operand inside a stage,
@@ -520,7 +523,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
       for (int c0 = 0; c0 < g.Npad; c0 += 16) {
         if (g.mode == 1) {
           // parity block qq = c0 / Cp of the 2x2 output pixels of this position; channel offset inside the block
-          const int qq = c0 / g.Cp, cc = c0 - qq * g.Cp;
+          const int qq = p.q0 + c0 / g.Cp, cc = c0 - (c0 / g.Cp) * g.Cp;
           yp = p.y + ((long)(px < 0 ? 0 : px) + (long)(qq >> 1) * p.W + (qq & 1)) * p.Cout - c0 + cc;
         }
         float v[16];
@@ -599,7 +602,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, uint8_t* __restrict_
 // Data gradient of a 3x3 / stride-2 / pad-1 convolution as ONE 2x2-tap stride-1 GEMM over dy whose N axis is the four
 // output-pixel parities: slab(tap=(du,dv), K step j): B[n = q*Cp + ci][c = co] = w[co][ci][r][s] with
 // (py,du) -> r : (0,0)->1, (1,0)->2, (1,1)->0, (0,1)->none ; same for (px,dv) -> s.
-__global__ void tc_pack_dgrad2_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, Geo g, int CoutW, int CinW) {
+__global__ void tc_pack_dgrad2_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, Geo g, int CoutW, int CinW, int q0) {
   const int nj = g.Cin16 / 16;
   const int step = blockIdx.x;
   const int tap = step / nj, j = step - tap * nj;
@@ -607,7 +610,7 @@ __global__ void tc_pack_dgrad2_kernel(const float* __restrict__ w, uint8_t* __re
   uint8_t* slab = out + (size_t)step * g.wslab;
   for (int e = threadIdx.x; e < g.Npad * 16; e += blockDim.x) {
     const int n = e >> 4, k = e & 15;
-    const int q = n / g.Cp, ci = n - q * g.Cp;
+    const int q = q0 + n / g.Cp, ci = n - (n / g.Cp) * g.Cp;
     const int py = q >> 1, px = q & 1;
     const int r = (py == 0) ? (du == 0 ? 1 : -1) : (du == 0 ? 2 : 0);
     const int sx = (px == 0) ? (dv == 0 ? 1 : -1) : (dv == 0 ? 2 : 0);
@@ -640,18 +643,21 @@ __global__ void tc_pack_batch_kernel(const PackJob* __restrict__ jobs, int njobs
   const int Cin = (int)jb.Cin, Cout = (int)jb.Cout, ks = (int)jb.ks, mode = (int)jb.mode;
   const int step = (int)((long long)blockIdx.x - jb.first);
   int Npad, Cin16, taps, Cp = 0;
-  if (mode == 2) { Cp = ceil_to(Cin, 16); Npad = 4 * Cp; Cin16 = ceil_to(Cout, 16); taps = 4; }   // (Cin, Cout) of the conv weight
+  int q0 = 0;
+  if (mode == 2) {                                               // (Cin, Cout) of the conv weight; ldw = q0 + 16*nqs
+    Cp = ceil_to(Cin, 16); Npad = (int)(jb.ldw >> 4) * Cp; q0 = (int)(jb.ldw & 15); Cin16 = ceil_to(Cout, 16); taps = 4;
+  }
   else { Npad = ceil_to(Cout, 16); Cin16 = ceil_to(Cin, 16); taps = ks * ks; }
   const int nj = Cin16 / 16;
   const int tap = step / nj, j = step - tap * nj;
   uint8_t* slab = reinterpret_cast<uint8_t*>(jb.out) + (size_t)step * 64 * Npad;
-  const int wCin = jb.ldw > 0 ? (int)jb.ldw : (mode == 1 ? Cout : Cin);
+  const int wCin = (mode != 2 && jb.ldw > 0) ? (int)jb.ldw : (mode == 1 ? Cout : Cin);
   for (int e = threadIdx.x; e < Npad * 16; e += blockDim.x) {
     const int n = e >> 4, k = e & 15;
     float v = 0.f;
     if (mode == 2) {
       const int du = tap >> 1, dv = tap & 1;
-      const int q = n / Cp, ci = n - q * Cp;
+      const int q = q0 + n / Cp, ci = n - (n / Cp) * Cp;
       const int py = q >> 1, px = q & 1;
       const int r = (py == 0) ? (du == 0 ? 1 : -1) : (du == 0 ? 2 : 0);
       const int sx = (px == 0) ? (dv == 0 ? 1 : -1) : (dv == 0 ? 2 : 0);
@@ -712,19 +718,28 @@ extern "C" {
 // ---- data gradient of a 3x3 stride-2 pad-1 convolution w[Cout][Cin][3][3]: dx[B,H,W,Cin] (+)= conv_transpose(dy[B,H/2,W/2,Cout])
 int hcm_tc_dgrad_s2_supported(int B, int H, int W, int Cin, int Cout) {
   if ((H | W) & 1) return 0;
-  Geo g = make_geo(B, H, W, Cout, Cin, 3, 2, 1);          // GEMM: K = Cout (channels of dy), N = 4 parities x Cin
+  Geo g = make_geo(B, H, W, Cout, Cin, 3, 2, 1);          // GEMM: K = Cout (channels of dy), N = parities x Cin
   return dgrad2_ok(g, H, W, Cout, Cin) ? 1 : 0;
 }
+// all parity groups' packs, consecutively (4/nqs groups of nsteps*wslab bytes)
 long hcm_tc_dgrad_s2_wpack_bytes(int B, int H, int W, int Cin, int Cout) {
   Geo g = make_geo(B, H, W, Cout, Cin, 3, 2, 1);
-  return (long)g.wbytes;
+  return (long)g.wbytes * (4 / g.nqs);
+}
+// parities per launch (4, 2 or 1): the pack buffer holds 4/nqs groups
+int hcm_tc_dgrad_s2_nqs(int B, int H, int W, int Cin, int Cout) {
+  Geo g = make_geo(B, H, W, Cout, Cin, 3, 2, 1);
+  return g.nqs;
 }
 int hcm_tc_dgrad_s2_pack(const float* w, void* wpack, int B, int H, int W, int Cin, int Cout, cudaStream_t stream) {
   HCM_CHECK_ARG(w && wpack, "tc_dgrad_s2_pack: null pointer");
   Geo g = make_geo(B, H, W, Cout, Cin, 3, 2, 1);
   HCM_CHECK_ARG(dgrad2_ok(g, H, W, Cout, Cin), "tc_dgrad_s2_pack: unsupported geometry");
-  tc_pack_dgrad2_kernel<<<g.nsteps, 256, 0, stream>>>(w, reinterpret_cast<uint8_t*>(wpack), g, Cout, Cin);
-  HCM_LAUNCH_CHECK("tc_dgrad_s2_pack");
+  for (int q0 = 0; q0 < 4; q0 += g.nqs) {
+    tc_pack_dgrad2_kernel<<<g.nsteps, 256, 0, stream>>>(w, reinterpret_cast<uint8_t*>(wpack) + (size_t)(q0 / g.nqs) * g.wbytes, g, Cout,
+                                                          Cin, q0);
+    HCM_LAUNCH_CHECK("tc_dgrad_s2_pack");
+  }
   return HCM_OK;
 }
 int hcm_tc_dgrad_s2(const float* dy, const void* wpack, float* dx, int B, int H, int W, int Cin, int Cout, int accumulate,
@@ -734,9 +749,15 @@ int hcm_tc_dgrad_s2(const float* dy, const void* wpack, float* dx, int B, int H,
   p.g = make_geo(B, H, W, Cout, Cin, 3, 2, 1);
   HCM_CHECK_ARG(dgrad2_ok(p.g, H, W, Cout, Cin), "tc_dgrad_s2: unsupported geometry (Cin=%d Cout=%d)", Cin, Cout);
   p.x = dy; p.in_scale = nullptr; p.in_shift = nullptr; p.in_relu = 0;
-  p.wpack = reinterpret_cast<const uint8_t*>(wpack); p.bias = nullptr; p.y = dx; p.accumulate = accumulate;
+  p.bias = nullptr; p.y = dx; p.accumulate = accumulate;
   p.B = B; p.H = H; p.W = W; p.Cin = Cout; p.Cout = Cin;   // as seen by the GEMM: staged channels = Cout(w), output channels = Cin(w)
-  return launch_tc(p, stream, "tc_dgrad_s2");
+  for (int q0 = 0; q0 < 4; q0 += p.g.nqs) {                 // disjoint output pixels per parity group
+    p.q0 = q0;
+    p.wpack = reinterpret_cast<const uint8_t*>(wpack) + (size_t)(q0 / p.g.nqs) * p.g.wbytes;
+    int rc = launch_tc(p, stream, "tc_dgrad_s2");
+    if (rc != HCM_OK) return rc;
+  }
+  return HCM_OK;
 }
 
 // One launch for all weight packs of a step.  jobs (device): njobs x 8 int64 {w ptr, out ptr, Cin, Cout, ks, mode, ldw, first_step}
@@ -789,7 +810,7 @@ int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, 
                 Cout, ks, stride);
   p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.in_relu = in_relu;
   p.wpack = reinterpret_cast<const uint8_t*>(wpack); p.bias = bias; p.y = y; p.accumulate = accumulate;
-  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.q0 = 0;
   return launch_tc(p, stream, "tc_conv");
 }
 

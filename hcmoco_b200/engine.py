@@ -338,7 +338,8 @@ class Engine:
             return
         for w, ldw, wp, (B, H, W), cin, cout, ks, mode in self.pack_jobs:
             if mode == 2:
-                K.tc_dgrad_s2_pack(w, wp, B, H, W, cin, cout)
+                if (ldw & 15) == 0:          # one call packs every parity group
+                    K.tc_dgrad_s2_pack(w, wp, B, H, W, cin, cout)
             else:
                 K.tc_conv_pack(w, ldw, wp, B, H, W, cin, cout, ks, mode)
 
@@ -419,8 +420,12 @@ class Engine:
                     self._pack_job(w, 0, wp_t, (B, H, W), cout, cin, ks, 1)
                     p.b(K.tc_conv, dy, wp_t, None, gx, B, H, W, cout, cin, ks, 1, None, None, 0, acc)
                 elif tc and stride == 2 and ks == 3 and K.tc_dgrad_s2_supported(B, H, W, cin, cout):
-                    wp_t = K.empty((K.tc_dgrad_s2_wpack_bytes(B, H, W, cin, cout) + 3) // 4)
-                    self._pack_job(w, 0, wp_t, (B, H, W), cin, cout, 3, 2)
+                    nbt2 = K.tc_dgrad_s2_wpack_bytes(B, H, W, cin, cout)
+                    wp_t = K.empty((nbt2 + 3) // 4)
+                    nqs = K.tc_dgrad_s2_nqs(B, H, W, cin, cout)
+                    per = nbt2 // (4 // nqs)
+                    for gi in range(4 // nqs):
+                        self._pack_job(w, gi * nqs + 16 * nqs, wp_t[gi * per // 4:], (B, H, W), cin, cout, 3, 2)
                     p.b(K.tc_dgrad_s2, dy, wp_t, gx, B, H, W, cin, cout, acc)
                 else:
                     p.b(K.conv2d_dgrad, dy, w, gx, B, H, W, cin, cout, ks, stride, acc)

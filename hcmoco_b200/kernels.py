@@ -42,7 +42,7 @@ class CudaKernels:
             else:
                 kinds.append("int")
         nuser = sum(1 for k in kinds if k != "stream")
-        returns_rows = name.endswith(("_rows", "_supported", "_bytes"))     # queries: return the value, launch nothing
+        returns_rows = name.endswith(("_rows", "_supported", "_bytes", "_nqs"))     # queries: return the value, launch nothing
 
         def call(*a):
             if len(a) != nuser:

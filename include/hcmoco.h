@@ -67,6 +67,7 @@ int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, 
  * N axis is the four output-pixel parities): dx[B,H,W,Cin] (+)= conv_transpose(dy[B,H/2,W/2,Cout], w) */
 int hcm_tc_dgrad_s2_supported(int B, int H, int W, int Cin, int Cout);
 long hcm_tc_dgrad_s2_wpack_bytes(int B, int H, int W, int Cin, int Cout);
+int hcm_tc_dgrad_s2_nqs(int B, int H, int W, int Cin, int Cout);   /* output parities per launch: 4, 2 or 1 */
 int hcm_tc_dgrad_s2_pack(const float* w, void* wpack, int B, int H, int W, int Cin, int Cout, cudaStream_t stream);
 int hcm_tc_dgrad_s2(const float* dy, const void* wpack, float* dx, int B, int H, int W, int Cin, int Cout, int accumulate,
                     cudaStream_t stream);

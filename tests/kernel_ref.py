@@ -131,7 +131,10 @@ class TorchKernels:
         return 0
 
     def tc_dgrad_s2_supported(self, B, H, W, Cin, Cout):
-        return int(H % 2 == 0 and W % 2 == 0 and Cin % 2 == 0 and Cout % 2 == 0 and Cin <= 64 and Cout <= 256)
+        return int(H % 2 == 0 and W % 2 == 0 and Cin % 2 == 0 and Cout % 2 == 0 and Cin <= 256 and Cout <= 256)
+
+    def tc_dgrad_s2_nqs(self, B, H, W, Cin, Cout):
+        return 4
 
     def tc_dgrad_s2_wpack_bytes(self, B, H, W, Cin, Cout):
         return Cin * Cout * 9 * 8

@@ -372,7 +372,7 @@ def test_tc_wgrad(KK, shape):
 
 
 TC_S2 = [(2, 32, 32, 18, 18), (2, 16, 16, 18, 36), (3, 8, 8, 36, 72), (2, 64, 64, 64, 64), (2, 16, 16, 72, 144), (2, 8, 8, 18, 144),
-         (4, 64, 64, 18, 18), (2, 32, 32, 32, 64)]
+         (4, 64, 64, 18, 18), (2, 32, 32, 32, 64), (2, 32, 32, 256, 36), (2, 8, 8, 128, 256), (2, 16, 16, 64, 128)]
 
 
 @pytest.mark.parametrize("shape", TC_S2)
@@ -396,11 +396,12 @@ def test_tc_conv_stride2(KK, shape):
 
 @pytest.mark.parametrize("shape", TC_S2)
 def test_tc_dgrad_stride2(KK, shape):
-    """data gradient of the stride-2 conv: one 2x2-tap GEMM over dy, N = 4 output parities x Cin."""
+    """data gradient of the stride-2 conv: one 2x2-tap GEMM over dy, N = nqs output parities x Cin
+    (4/nqs launches when 4*Cin does not fit N <= 256)."""
     B, H, W, Cin, Cout = shape
     kc, kr = KK
     if not kc.tc_dgrad_s2_supported(B, H, W, Cin, Cout):
-        pytest.skip("N = 4*ceil16(Cin) > 256")
+        pytest.skip("ceil16(Cin) > 256")
     w, dy = rnd(Cout, Cin, 3, 3, scale=0.1), rnd(B, H // 2, W // 2, Cout, seed=3)
     wp = torch.zeros((kc.tc_dgrad_s2_wpack_bytes(B, H, W, Cin, Cout) + 3) // 4, device=DEV)
     kc.tc_dgrad_s2_pack(w, wp, B, H, W, Cin, Cout)
