@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--nce-k", type=int, default=16384)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="profiling aid: after the warm-up run ONE step between cudaProfilerStart/Stop and exit "
+                         "(use with `ncu --profile-from-start off`); prints no bench line")
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--detail", default=None, help="write the per-shape conv timing table to this file")
     return ap.parse_args()
@@ -217,6 +220,13 @@ def run_engine(a):
 
     for i in range(a.warmup):
         step.run(dev[i % 2])
+    if a.ncu_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step.run(dev[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()

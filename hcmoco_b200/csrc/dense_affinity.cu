@@ -1,0 +1,399 @@
+// Fused dense intra-sample affinity objective (learning/contrast_trainer.py:642-723), forward and backward.
+//
+//   a_j = norm(G1[b, pix_j, :])   d_i = norm(G2[b, pix_i, :])   L[i][j] = <d_i, a_j> / T      (S sampled pixels, C = 128)
+//   loss_r2d = -mean_j sum_i W[i][j] log_softmax_i L[i][j]      loss_d2r = the same on L^T     W = softmax_i(-|c_i - c_j|)
+//
+// One CTA owns (sample b, side, strip of <=128 rows).  side 0: strip rows are the a_j (statistics of the COLUMNS of L),
+// the other operand is all d_i; side 1: strip rows are the d_i (statistics of the ROWS of L), the other operand all a_j.
+// Computing both L-strips and L^T-strips on the tensor cores makes every softmax statistic a per-row (= per TMEM lane)
+// reduction: no cross-lane shuffles, no cross-CTA combine, and nothing S x S is ever written to HBM.
+//
+//   gather (512 B coalesced rows of the channels-last maps) -> L2-normalise -> bf16 hi/lo split -> shared memory in the
+//   UMMA no-swizzle K-major layout -> tcgen05.mma (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM) per chunk of NC
+//   columns -> tcgen05.ld epilogue: online soft-target log-softmax statistics (forward) or the logit gradient
+//   G = coef*(softmax_own + softmax_other - W_own - W_other), which goes back to shared memory as the A operand of a second
+//   MMA  dXn = G * Y  (Y re-used in place as an MN-major B operand), then the L2-norm backward and a coalesced
+//   atomic scatter into the map gradient (sampled pixels repeat).
+//
+// Algorithmic HBM bytes per depth-bearing triplet: 2*S*128*4 gathered features (+2*S*8 indices); the redundant re-gathers of
+// the "other" operand by the strips of a sample hit L2.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int DA_C = 128;          // feature channels
+constexpr int DA_THREADS = 256;
+constexpr int DA_HDR = 1024;
+
+struct DaGeo {
+  int S, h, HW, nstrips, RS, nchunks, NC, Spad;
+  uint32_t lbo_x, lbo_y;            // K-direction core-matrix strides (bytes) of the strip / chunk slabs
+  uint32_t off_tab, off_red, off_x, off_y, off_g, smem_bytes;
+};
+
+DaGeo da_geo(int S, int h, bool bwd) {
+  DaGeo g;
+  g.S = S; g.h = h; g.HW = h * h;
+  g.nstrips = (S + 127) / 128;
+  g.RS = (S + g.nstrips - 1) / g.nstrips;
+  g.nchunks = (S + 127) / 128;
+  g.NC = ceil_to((S + g.nchunks - 1) / g.nchunks, 16);
+  g.Spad = g.nchunks * g.NC;
+  g.lbo_x = 128 * 16 + 16;
+  g.lbo_y = (uint32_t)g.NC * 16 + 16;
+  uint32_t o = DA_HDR;
+  g.off_tab = o; o += (uint32_t)g.Spad * 4 * 4;                  // cy, cx, lse_other, zinv_other
+  g.off_red = o; o += 128 * 8 * 4;
+  o = (o + 127) / 128 * 128;
+  g.off_x = o; o += 2 * 16 * g.lbo_x;                            // X hi | X lo   (also the fp32 staging of the scatter)
+  g.off_y = o; o += 2 * 16 * g.lbo_y;                            // Y hi | Y lo
+  g.off_g = o; if (bwd) o += 2 * (uint32_t)(g.NC / 8) * g.lbo_x; // G hi | G lo
+  g.smem_bytes = o;
+  return g;
+}
+
+struct DaParams {
+  const float* G1; const float* G2;
+  const long long* pix; const float* kept; const float* fin;
+  float* stat;                     // [B][2][S][4] = (lse, Z, sum w*logit, first-argmax hit)
+  float* dG1; float* dG2;
+  float inv_T, gscale;
+  DaGeo g;
+};
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// kind::f16 instruction descriptor: D fp32, A/B bf16, M = 128; b_mn = 1 -> B operand MN-major
+__device__ __forceinline__ uint32_t da_idesc(int N, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// Stage rows [first, first + nrows) of one sample (row r valid if first + r < last): gather 128 channels from the
+// channels-last map, L2-normalise (F.normalize, eps 1e-12), split into bf16 hi / lo, write both K-major slabs
+// ([channel/8][row][8 channels], chunk stride lbo).  One warp per row, 4 rows in flight per warp.
+__device__ __forceinline__ void da_stage(const float* __restrict__ map_b, const long long* __restrict__ pix_b, int first, int last,
+                                         int nrows, uint8_t* hi, uint8_t* lo, uint32_t lbo, int warp, int lane) {
+  for (int r0 = warp * 4; r0 < nrows; r0 += (DA_THREADS / 32) * 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u, gr = first + r;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nrows && gr < last) v[u] = __ldg(reinterpret_cast<const float4*>(map_b + pix_b[gr] * DA_C + 4 * lane));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u;
+      if (r >= nrows) break;
+      const float ss = warp_sum(v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w);
+      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      const float x0 = v[u].x * inv, x1 = v[u].y * inv, x2 = v[u].z * inv, x3 = v[u].w * inv;
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1), h2 = __float2bfloat16_rn(x2),
+                          h3 = __float2bfloat16_rn(x3);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1)),
+                          l2 = __float2bfloat16_rn(x2 - __bfloat162float(h2)), l3 = __float2bfloat16_rn(x3 - __bfloat162float(h3));
+      const uint32_t off = (uint32_t)(lane >> 1) * lbo + (uint32_t)r * 16 + (uint32_t)(lane & 1) * 8;
+      *reinterpret_cast<uint2*>(hi + off) =
+          make_uint2((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16),
+                     (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16));
+      *reinterpret_cast<uint2*>(lo + off) =
+          make_uint2((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16),
+                     (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16));
+    }
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const DaGeo& g = p.g;
+  const int b = blockIdx.z, side = blockIdx.y, strip = blockIdx.x;
+  if (p.kept[b] == 0.f) return;
+  float coef = 0.f;
+  if (BWD) {
+    const float nk = p.fin[4];
+    if (!(nk > 0.f)) return;
+    coef = p.gscale / (nk * (float)g.S);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = g.S;
+  const int row0 = strip * g.RS, row_end = min(S, row0 + g.RS);
+  // side 0: strip = rgb rows (G1), other = depth (G2); side 1: strip = depth rows, other = rgb
+  const float* Xmap = (side == 0 ? p.G1 : p.G2) + (long)b * g.HW * DA_C;
+  const float* Ymap = (side == 0 ? p.G2 : p.G1) + (long)b * g.HW * DA_C;
+  const long long* pix_b = p.pix + (long)b * S;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + 64);
+  float* s_cy = reinterpret_cast<float*>(smem + g.off_tab);
+  float* s_cx = s_cy + g.Spad;
+  float* s_lse_o = s_cx + g.Spad;
+  float* s_zinv_o = s_lse_o + g.Spad;
+  float* s_red = reinterpret_cast<float*>(smem + g.off_red);
+  uint8_t* Xhi = smem + g.off_x;
+  uint8_t* Xlo = Xhi + 16 * g.lbo_x;
+  uint8_t* Yhi = smem + g.off_y;
+  uint8_t* Ylo = Yhi + 16 * g.lbo_y;
+  uint8_t* Ghi = smem + g.off_g;
+  uint8_t* Glo = Ghi + (uint32_t)(g.NC / 8) * g.lbo_x;
+  const uint32_t bar1 = smem_u32(bars), bar2 = bar1 + 8;
+  const uint32_t tmem_cols = BWD ? 256u : 128u;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar1, 1);
+    mbar_init(bar2, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_ptr), tmem_cols);
+  for (int q = threadIdx.x; q < g.Spad; q += DA_THREADS) {
+    const long long px = q < S ? pix_b[q] : 0;
+    s_cy[q] = (float)(px / g.h);
+    s_cx[q] = (float)(px % g.h);
+    if (BWD) {
+      const float* so = p.stat + (((long)b * 2 + (1 - side)) * S + (q < S ? q : 0)) * 4;
+      s_lse_o[q] = so[0];
+      s_zinv_o[q] = 1.f / so[1];
+    }
+  }
+  da_stage(Xmap, pix_b, row0, row_end, 128, Xhi, Xlo, g.lbo_x, warp, lane);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tP = tmem, tdX = tmem + 128;
+
+  // this thread's strip row (TMEM lane) and column half
+  const int qtr = warp & 3, half = warp >> 2;
+  const int row = qtr * 32 + lane;
+  const int grow = row0 + row;
+  const bool row_ok = grow < row_end;
+  const float my_y = s_cy[row_ok ? grow : 0], my_x = s_cx[row_ok ? grow : 0];
+  float lse_own = 0.f, zinv_own = 0.f;
+  if (BWD && row_ok) {
+    const float* so = p.stat + (((long)b * 2 + side) * S + grow) * 4;
+    lse_own = so[0];
+    zinv_own = 1.f / so[1];
+  }
+  float mx = -INFINITY, se = 0.f, Z = 0.f, wl = 0.f;
+  int am = 0;
+  const int hc = g.NC / 2;                       // columns per half (multiple of 8)
+  const uint32_t idesc1 = da_idesc(g.NC, 0), idesc2 = da_idesc(128, 1);
+  uint32_t ph1 = 0, ph2 = 0;
+
+  for (int c = 0; c < g.nchunks; ++c) {
+    da_stage(Ymap, pix_b, c * g.NC, S, g.NC, Yhi, Ylo, g.lbo_y, warp, lane);
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t xh = smem_u32(Xhi), xl = smem_u32(Xlo), yh = smem_u32(Yhi), yl = smem_u32(Ylo);
+#pragma unroll 1
+        for (int k = 0; k < DA_C / 16; ++k) {
+          const uint64_t ah = smem_desc(xh + 2 * k * g.lbo_x, g.lbo_x, 128), al = smem_desc(xl + 2 * k * g.lbo_x, g.lbo_x, 128);
+          const uint64_t bh = smem_desc(yh + 2 * k * g.lbo_y, g.lbo_y, 128), bl = smem_desc(yl + 2 * k * g.lbo_y, g.lbo_y, 128);
+          umma_bf16(tP, ah, bh, idesc1, k > 0 ? 1u : 0u);
+          umma_bf16(tP, al, bh, idesc1, 1u);
+          umma_bf16(tP, ah, bl, idesc1, 1u);
+        }
+        umma_commit(bar1);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar1, ph1);
+    ph1 ^= 1;
+    tc_fence_after();
+
+    // ---- epilogue over this thread's half of the chunk columns
+    for (int c0 = half * hc; c0 < (half + 1) * hc; c0 += 8) {
+      float v[8];
+      tmem_ld8(tP + ((uint32_t)(qtr * 32) << 16) + (uint32_t)c0, v);
+      const int q0 = c * g.NC + c0;
+      if (!BWD) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int q = q0 + i;
+          if (q < S) {
+            const float l = v[i] * p.inv_T;
+            const float dy = s_cy[q] - my_y, dx = s_cx[q] - my_x;
+            const float w = __expf(-sqrtf(dy * dy + dx * dx));
+            Z += w;
+            wl = fmaf(w, l, wl);
+            if (l > mx) { se = se * __expf(mx - l) + 1.f; mx = l; am = q; }
+            else se += __expf(l - mx);
+          }
+        }
+      } else {
+        float gv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int q = q0 + i;
+          float gg = 0.f;
+          if (q < S && row_ok) {
+            const float l = v[i] * p.inv_T;
+            const float dy = s_cy[q] - my_y, dx = s_cx[q] - my_x;
+            const float w = __expf(-sqrtf(dy * dy + dx * dx));
+            gg = coef * (__expf(l - lse_own) + __expf(l - s_lse_o[q]) - w * (zinv_own + s_zinv_o[q]));
+          }
+          gv[i] = gg;
+        }
+        uint4 gh, gl;
+        split8(gv, gh, gl);
+        const uint32_t off = (uint32_t)(c0 >> 3) * g.lbo_x + (uint32_t)row * 16;
+        *reinterpret_cast<uint4*>(Ghi + off) = gh;
+        *reinterpret_cast<uint4*>(Glo + off) = gl;
+      }
+    }
+    tc_fence_before();
+    if (BWD) {
+      // ---- dXn[row][ch] += sum_q G[row][q] * Y[q][ch]   (A = G K-major, B = the staged Y slab read MN-major)
+      fence_proxy_async();
+      __syncthreads();
+      if (warp == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t gh = smem_u32(Ghi), gl = smem_u32(Glo), yh = smem_u32(Yhi), yl = smem_u32(Ylo);
+          // MN-major no-swizzle canonical layout ((1,n),(8,k)):((X,SBO),(1,LBO)) in 16-byte units: the 16-byte channel
+          // blocks are SBO = lbo_y apart, the 8-row K groups LBO = 128 bytes apart (roles swapped w.r.t. K-major; verified
+          // on B200 against the fp32 statement)
+          const uint32_t b_lbo = 128u, b_sbo = g.lbo_y;
+#pragma unroll 1
+          for (int ks = 0; ks < g.NC / 16; ++ks) {
+            const uint64_t ah = smem_desc(gh + 2 * ks * g.lbo_x, g.lbo_x, 128), al = smem_desc(gl + 2 * ks * g.lbo_x, g.lbo_x, 128);
+            const uint64_t bh = smem_desc(yh + ks * 256, b_lbo, b_sbo), bl = smem_desc(yl + ks * 256, b_lbo, b_sbo);
+            umma_bf16(tdX, ah, bh, idesc2, (c > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16(tdX, al, bh, idesc2, 1u);
+            umma_bf16(tdX, ah, bl, idesc2, 1u);
+          }
+          umma_commit(bar2);
+        }
+        __syncwarp();
+      }
+      mbar_wait(bar2, ph2);
+      ph2 ^= 1;
+      tc_fence_after();
+    } else {
+      __syncthreads();         // every warp has drained P before the next chunk's MMAs overwrite it (and Y is restaged)
+    }
+  }
+
+  if (!BWD) {
+    // ---- combine the two column halves of every row; first maximal index wins (torch.argmax)
+    if (half == 1) {
+      float* r = s_red + row * 8;
+      r[0] = mx; r[1] = se; r[2] = Z; r[3] = wl; r[4] = __int_as_float(am);
+    }
+    __syncthreads();
+    if (half == 0 && row_ok) {
+      const float* r = s_red + row * 8;
+      const float mx2 = r[0], se2 = r[1];
+      const int am2 = __float_as_int(r[4]);
+      const float m = fmaxf(mx, mx2);
+      const float s = se * __expf(mx - m) + se2 * __expf(mx2 - m);
+      int a = am;
+      if (mx2 > mx || (mx2 == mx && am2 < am)) a = am2;
+      float* o = p.stat + (((long)b * 2 + side) * S + grow) * 4;
+      o[0] = m + logf(s);
+      o[1] = Z + r[2];
+      o[2] = wl + r[3];
+      o[3] = (a == grow) ? 1.f : 0.f;
+    }
+  } else {
+    // ---- L2-norm backward of the strip rows: dx = inv_T * (dXn - xn <dXn, xn>) / |x|, then atomic scatter
+    const float* xrow = Xmap + (row_ok ? pix_b[grow] : 0) * DA_C + half * 64;
+    float dot = 0.f, ss = 0.f;
+    for (int c0 = 0; c0 < 64; c0 += 8) {
+      float v[8];
+      tmem_ld8(tdX + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(half * 64 + c0), v);
+      const float4 xa = __ldg(reinterpret_cast<const float4*>(xrow + c0)), xb = __ldg(reinterpret_cast<const float4*>(xrow + c0 + 4));
+      const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { dot = fmaf(v[i], x[i], dot); ss = fmaf(x[i], x[i], ss); }
+    }
+    s_red[(half * 128 + row) * 2 + 0] = dot;
+    s_red[(half * 128 + row) * 2 + 1] = ss;
+    __syncthreads();                                  // also: all MMAs are complete, the X slabs are free
+    dot = s_red[row * 2] + s_red[(128 + row) * 2];
+    ss = s_red[row * 2 + 1] + s_red[(128 + row) * 2 + 1];
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    const float dotn = dot * inv;                     // <dXn, xn>
+    float* stage = reinterpret_cast<float*>(Xhi);     // [128][129] fp32
+    for (int c0 = 0; c0 < 64; c0 += 8) {
+      float v[8];
+      tmem_ld8(tdX + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(half * 64 + c0), v);
+      const float4 xa = __ldg(reinterpret_cast<const float4*>(xrow + c0)), xb = __ldg(reinterpret_cast<const float4*>(xrow + c0 + 4));
+      const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) stage[row * 129 + half * 64 + c0 + i] = p.inv_T * (v[i] - x[i] * inv * dotn) * inv;
+    }
+    __syncthreads();
+    float* dmap = (side == 0 ? p.dG1 : p.dG2) + (long)b * g.HW * DA_C;
+    for (int r = warp; r < row_end - row0; r += DA_THREADS / 32) {
+      float* dst = dmap + pix_b[row0 + r] * DA_C;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(dst + lane + 32 * i, stage[r * 129 + lane + 32 * i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+}  // namespace
+
+extern "C" {
+
+int hcm_dense_finish(const float* stat, const float* kept, const long long* use_depth, int B, int S, float* fin,
+                     cudaStream_t stream);
+
+// stat [B][2][S][4] scratch (kept for the backward); fin[5] = loss_r2d, loss_d2r, acc_r2d, acc_d2r, B'
+int hcm_dense_affinity_fwd(const float* G1, const float* G2, const long long* pix, const float* kept,
+                           const long long* use_depth, int B, int S, int h, int dim, float inv_T, float* stat, float* fin,
+                           cudaStream_t stream) {
+  HCM_CHECK_ARG(G1 && G2 && pix && kept && stat && fin, "dense_affinity_fwd: null pointer");
+  HCM_CHECK_ARG(dim == DA_C && B >= 1 && S >= 1 && h >= 1, "dense_affinity_fwd: bad args (dim=%d B=%d S=%d h=%d)", dim, B, S, h);
+  DaParams p = {};
+  p.G1 = G1; p.G2 = G2; p.pix = pix; p.kept = kept; p.stat = stat; p.inv_T = inv_T;
+  p.g = da_geo(S, h, false);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(dense_affinity_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  dim3 grid(p.g.nstrips, 2, B);
+  dense_affinity_kernel<false><<<grid, DA_THREADS, p.g.smem_bytes, stream>>>(p);
+  HCM_LAUNCH_CHECK("dense_affinity_fwd");
+  return hcm_dense_finish(stat, kept, use_depth, B, S, fin, stream);
+}
+
+// dG1, dG2 [B][h*h][128] are ACCUMULATED into (atomics: sampled pixels repeat); the caller zeroes them
+int hcm_dense_affinity_bwd(const float* G1, const float* G2, const long long* pix, const float* stat, const float* kept,
+                           const float* fin, int B, int S, int h, int dim, float inv_T, float gscale, float* dG1, float* dG2,
+                           cudaStream_t stream) {
+  HCM_CHECK_ARG(G1 && G2 && pix && stat && kept && fin && dG1 && dG2, "dense_affinity_bwd: null pointer");
+  HCM_CHECK_ARG(dim == DA_C && B >= 1 && S >= 1 && h >= 1, "dense_affinity_bwd: bad args (dim=%d B=%d S=%d h=%d)", dim, B, S, h);
+  DaParams p = {};
+  p.G1 = G1; p.G2 = G2; p.pix = pix; p.kept = kept; p.fin = fin; p.stat = const_cast<float*>(stat);
+  p.dG1 = dG1; p.dG2 = dG2; p.inv_T = inv_T; p.gscale = gscale;
+  p.g = da_geo(S, h, true);
+  HCM_CHECK_ARG(p.g.smem_bytes <= 227 * 1024, "dense_affinity_bwd: shared memory (%u bytes)", p.g.smem_bytes);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(dense_affinity_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr = true;
+  }
+  dim3 grid(p.g.nstrips, 2, B);
+  dense_affinity_kernel<true><<<grid, DA_THREADS, p.g.smem_bytes, stream>>>(p);
+  HCM_LAUNCH_CHECK("dense_affinity_bwd");
+  return HCM_OK;
+}
+
+}  // extern "C"

@@ -352,6 +352,15 @@ int hcm_dense_stats(const float* L, const long long* pix, const float* kept, con
   return HCM_OK;
 }
 
+// fin[5] from stat [B][2][S][4] (shared by the unfused statistics above and the fused kernel in dense_affinity.cu)
+int hcm_dense_finish(const float* stat, const float* kept, const long long* use_depth, int B, int S, float* fin,
+                     cudaStream_t stream) {
+  HCM_CHECK_ARG(stat && kept && fin, "dense_finish: null pointer");
+  dense_finish_kernel<<<1, 256, 0, stream>>>(stat, kept, use_depth, B, S, fin);
+  HCM_LAUNCH_CHECK("dense_finish");
+  return HCM_OK;
+}
+
 int hcm_dense_grad(float* L, const long long* pix, const float* stat, const float* kept, const float* fin, int B, int S,
                    int h, float gscale, cudaStream_t stream) {
   HCM_CHECK_ARG(L && pix && stat && kept && fin, "dense_grad: null pointer");

@@ -98,5 +98,91 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// byte offset of 16-byte chunk `kb` (multiple of 16, < SW) of row `row` inside a swizzled plane (rows of SW bytes, 1024-B aligned
+// base): Swizzle<log2(SW/16),4,3> — the chunk index is XORed with address bits [7, 7+log2(SW/16))
+__device__ __forceinline__ uint32_t swz16(uint32_t row, uint32_t kb, uint32_t SW) {
+  const uint32_t off = row * SW;
+  return off + ((((kb >> 4) ^ (off >> 7)) & (SW / 16 - 1)) << 4);
+}
+
+// Stage `nch` channels [c_first, c_first + nch) of `rows` positions (src_tab[row * tab_stride + tab_off] = source pixel, < 0:
+// padding -> zeros) of a channels-last fp32 tensor into a swizzled bf16 hi / lo tile pair: rows of SW bytes per plane, the
+// first channel at byte `byte0` (multiple of 16) of the staged row, planes `plane` bytes apart, lo tile `lo_off` after hi.
+// The optional per-channel affine (+ReLU) is the producer's pending BatchNorm.
+// Work item = (row, 8-channel chunk) = one 16-byte hi chunk + one 16-byte lo chunk.  A thread keeps ONE chunk for the whole
+// call (channel offset, destination column and the 8+8 BN coefficients live in registers) and walks the rows, two rows
+// (up to 8 loads) in flight: ~9 instructions per channel instead of the ~57 of a (row, 2-4 channel) unit with per-unit
+// table lookups.  Consecutive lanes read consecutive chunks of a row, then the next row: fully coalesced.
+// V = 4: 16-byte loads (C % 4 == 0), V = 2: 8-byte loads (C even).  Threads t in [0, TS) of one team call it together.
+template <int V>
+__device__ __forceinline__ void stage_rows8(const float* __restrict__ src, int C, int c_first, int nch, int rows,
+                                            const int* __restrict__ src_tab, int tab_stride, int tab_off, uint8_t* hi_base,
+                                            uint32_t lo_off, uint32_t plane, uint32_t SW, uint32_t byte0, const float* s_sc,
+                                            const float* s_sh, bool affine, int relu, int t, int TS) {
+  const int cpp = (nch + 7) >> 3;                       // chunks per row
+  const int dpos = TS / cpp;                            // rows advanced per step (TS >= 128 >= cpp)
+  if (t >= dpos * cpp) return;
+  const int pos0 = t / cpp, ch = t - pos0 * cpp;
+  const int c = c_first + ch * 8;
+  const int nval = min(8, nch - ch * 8);
+  const uint32_t kb = byte0 + (uint32_t)ch * 16;
+  uint8_t* hi = hi_base + (kb / SW) * plane;
+  const uint32_t kbin = kb % SW;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool ok = affine && i < nval;
+    sc[i] = ok ? s_sc[c + i] : 0.f;
+    sh[i] = ok ? s_sh[c + i] : 0.f;
+  }
+  const float* srcc = src + c;
+  const int* tab = src_tab + tab_off;
+  for (int pos = pos0; pos < rows; pos += 2 * dpos) {
+    float v[2][8];
+    int px[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int pp = pos + u * dpos;
+      px[u] = pp < rows ? tab[pp * tab_stride] : -2;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+      if (px[u] >= 0) {
+        const float* xp = srcc + (long)px[u] * C;
+        if (V == 4) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(xp));
+          v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
+          if (nval > 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(xp + 4));
+            v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (2 * j < nval) {
+              const float2 a = __ldg(reinterpret_cast<const float2*>(xp + 2 * j));
+              v[u][2 * j] = a.x; v[u][2 * j + 1] = a.y;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (px[u] == -2) continue;
+      if (affine && px[u] >= 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a = fmaf(v[u][i], sc[i], sh[i]);
+          v[u][i] = relu ? fmaxf(a, 0.f) : a;
+        }
+      }
+      uint4 h, l;
+      split8(v[u], h, l);
+      const uint32_t off = swz16((uint32_t)(pos + u * dpos), kbin, SW);
+      *reinterpret_cast<uint4*>(hi + off) = h;
+      *reinterpret_cast<uint4*>(hi + lo_off + off) = l;
+    }
+  }
+}
 
 }  // namespace

@@ -414,91 +414,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
           const int pos = e / g.nq, q = e - pos * g.nq;
           src_tab[e] = (pos < g.L) ? virt_to_src(tile0 - g.center + pos, q, p) : -1;
         }
-        // unit table of this group: the real (non-padding) channel units [V channels] it stages
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TS) : "memory");
+        // the real (non-padding) channels of this group, plane by plane (stride 2: four parity planes side by side)
         const int c_lo = grp * g.cg, c_hi = c_lo + g.cg;
-        int upp = 0;                                                       // units per position
+        uint8_t* A_hi = Abase + (size_t)s * g.a_stage_bytes;
         for (int q = 0; q < g.nq; ++q) {
           const int a = max(c_lo, q * g.Cin16), b = min(c_hi, q * g.Cin16 + p.Cin);
-          if (b > a) upp += (b - a) / V;
-        }
-        {
-          if (t < upp) {
-            int rem = t, q = 0, cs = 0;
-            for (q = 0; q < g.nq; ++q) {
-              const int a = max(c_lo, q * g.Cin16), b = min(c_hi, q * g.Cin16 + p.Cin);
-              const int n = b > a ? (b - a) / V : 0;
-              if (rem < n) { cs = a + rem * V; break; }
-              rem -= n;
-            }
-            const int csrc = cs - q * g.Cin16, cl = cs - c_lo;
-            // packed: plane q (2 bits) | source channel (10 bits) | staged block (4 bits) | byte within row block (8 bits)
-            s_unit[team * MAX_UNITS + t] = q | (csrc << 2) | ((cl / g.KB) << 12) | (((cl % g.KB) * 2) << 16);
-          }
-        }
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TS) : "memory");
-        uint8_t* A_hi = Abase + (size_t)s * g.a_stage_bytes;
-        const int total = upp * g.Lpad;
-        const int dpos = TS / upp, drc = TS - dpos * upp;
-        int pos = t / upp, rc = t - pos * upp;
-        for (int e0 = t; e0 < total; e0 += 4 * TS) {
-          float v[4][4];
-          uint32_t dst[4];
-          int csrcv[4];
-          bool act[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            act[u] = (e0 + u * TS) < total;
-            const int un = s_unit[team * MAX_UNITS + (act[u] ? rc : 0)];
-            const int q = un & 3, csrc = (un >> 2) & 1023;
-            csrcv[u] = csrc;
-            dst[u] = (uint32_t)((un >> 12) & 15) * plane + swz((uint32_t)(act[u] ? pos : 0), (uint32_t)(un >> 16), SW);
-            const int px = act[u] ? src_tab[pos * g.nq + q] : -1;
-            v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
-            if (px >= 0) {
-              const float* xp = p.x + (long)px * p.Cin + csrc;
-              if (V == 4) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(xp));
-                v[u][0] = w4.x; v[u][1] = w4.y; v[u][2] = w4.z; v[u][3] = w4.w;
-              } else {
-                const float2 w2 = __ldg(reinterpret_cast<const float2*>(xp));
-                v[u][0] = w2.x; v[u][1] = w2.y;
-              }
-            } else {
-              csrcv[u] = -1;
-            }
-            // advance (pos, rc) by TS units
-            pos += dpos; rc += drc;
-            if (rc >= upp) { rc -= upp; ++pos; }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (!act[u]) continue;
-            if (p.in_scale && csrcv[u] >= 0) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (i < V) {
-                  const float a = fmaf(v[u][i], s_sc[csrcv[u] + i], s_sh[csrcv[u] + i]);
-                  v[u][i] = p.in_relu ? fmaxf(a, 0.f) : a;
-                }
-              }
-            }
-            uint32_t h[2], l[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(v[u][2 * i]), h1 = __float2bfloat16_rn(v[u][2 * i + 1]);
-              const __nv_bfloat16 l0 = __float2bfloat16_rn(v[u][2 * i] - __bfloat162float(h0));
-              const __nv_bfloat16 l1 = __float2bfloat16_rn(v[u][2 * i + 1] - __bfloat162float(h1));
-              h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-              l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-            }
-            if (V == 4) {
-              *reinterpret_cast<uint2*>(A_hi + dst[u]) = make_uint2(h[0], h[1]);
-              *reinterpret_cast<uint2*>(A_hi + lo_off + dst[u]) = make_uint2(l[0], l[1]);
-            } else {
-              *reinterpret_cast<uint32_t*>(A_hi + dst[u]) = h[0];
-              *reinterpret_cast<uint32_t*>(A_hi + lo_off + dst[u]) = l[0];
-            }
-          }
+          if (b <= a) continue;
+          if (V == 4) stage_rows8<4>(p.x, p.Cin, a - q * g.Cin16, b - a, g.Lpad, src_tab, g.nq, q, A_hi, lo_off, plane, SW,
+                                     (uint32_t)(a - c_lo) * 2, s_sc, s_sh, p.in_scale != nullptr, p.in_relu, t, TS);
+          else stage_rows8<2>(p.x, p.Cin, a - q * g.Cin16, b - a, g.Lpad, src_tab, g.nq, q, A_hi, lo_off, plane, SW,
+                              (uint32_t)(a - c_lo) * 2, s_sc, s_sh, p.in_scale != nullptr, p.in_relu, t, TS);
         }
         fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         mbar_arrive(BAR(s));

@@ -131,78 +131,6 @@ __device__ __forceinline__ void virt_decode(long pv, const WParams& p, int& src0
   dst = (int)((b * g.Ho + row - 1) * g.Wo + (col - 1));
 }
 
-// stage V channels (fp32 -> bf16 hi/lo) of one (row, channel) unit into a swizzled tile
-template <int V>
-__device__ __forceinline__ void put_unit(const float* v, uint8_t* hi_base, uint32_t lo_off, uint32_t dst) {
-  uint32_t h[2], l[2];
-#pragma unroll
-  for (int i = 0; i < V / 2; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  }
-  if (V == 4) {
-    *reinterpret_cast<uint2*>(hi_base + dst) = make_uint2(h[0], h[1]);
-    *reinterpret_cast<uint2*>(hi_base + lo_off + dst) = make_uint2(l[0], l[1]);
-  } else {
-    *reinterpret_cast<uint32_t*>(hi_base + dst) = h[0];
-    *reinterpret_cast<uint32_t*>(hi_base + lo_off + dst) = l[0];
-  }
-}
-
-// gather `nch` channels starting at c_first of `rows` positions into a swizzled tile; src_tab[row] = pixel or -1
-template <int V>
-__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int C, int c_first, int nch, int rows, const int* src_tab,
-                                           int tab_stride, int tab_off, uint8_t* hi_base, uint32_t lo_off, uint32_t plane, uint32_t SW,
-                                           uint32_t byte0, const float* s_sc, const float* s_sh, bool affine, int relu, int t, int TS) {
-  const int upp = nch / V;                               // units per row
-  const int total = upp * rows;
-  const int dpos = TS / upp, drc = TS - dpos * upp;
-  int pos = t / upp, rc = t - pos * upp;
-  for (int e0 = t; e0 < total; e0 += 4 * TS) {
-    float v[4][4];
-    uint32_t dst[4];
-    int cs[4];
-    bool act[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      act[u] = (e0 + u * TS) < total;
-      const int c = c_first + rc * V;
-      const uint32_t kb = byte0 + (uint32_t)(rc * V) * 2;              // byte inside the staged row (all blocks)
-      dst[u] = (kb / SW) * plane + swz((uint32_t)(act[u] ? pos : 0), kb % SW, SW);
-      const int px = act[u] ? src_tab[pos * tab_stride + tab_off] : -1;
-      cs[u] = (px >= 0) ? c : -1;
-      v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
-      if (px >= 0) {
-        const float* xp = src + (long)px * C + c;
-        if (V == 4) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(xp));
-          v[u][0] = w4.x; v[u][1] = w4.y; v[u][2] = w4.z; v[u][3] = w4.w;
-        } else {
-          const float2 w2 = __ldg(reinterpret_cast<const float2*>(xp));
-          v[u][0] = w2.x; v[u][1] = w2.y;
-        }
-      }
-      pos += dpos; rc += drc;
-      if (rc >= upp) { rc -= upp; ++pos; }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (!act[u]) continue;
-      if (affine && cs[u] >= 0) {
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const float a = fmaf(v[u][i], s_sc[cs[u] + i], s_sh[cs[u] + i]);
-          v[u][i] = relu ? fmaxf(a, 0.f) : a;
-        }
-      }
-      put_unit<V>(v[u], hi_base, lo_off, dst[u]);
-    }
-  }
-}
-
 __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const WGeo& g = p.g;
@@ -320,13 +248,13 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
       asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TS) : "memory");
       uint8_t* st = Sbase + (size_t)s * g.stage_bytes;
       // dy tile: channels [co_lo, co_lo + co_n)
-      if (g.Vd == 4) stage_rows<4>(p.dy, p.Cout, co_lo, co_n, TILE, dtab, 1, 0, st, d_lo, (uint32_t)g.d_plane, SWd, 0, nullptr, nullptr, false, 0, t, TS);
-      else stage_rows<2>(p.dy, p.Cout, co_lo, co_n, TILE, dtab, 1, 0, st, d_lo, (uint32_t)g.d_plane, SWd, 0, nullptr, nullptr, false, 0, t, TS);
+      if (g.Vd == 4) stage_rows8<4>(p.dy, p.Cout, co_lo, co_n, TILE, dtab, 1, 0, st, d_lo, (uint32_t)g.d_plane, SWd, 0, nullptr, nullptr, false, 0, t, TS);
+      else stage_rows8<2>(p.dy, p.Cout, co_lo, co_n, TILE, dtab, 1, 0, st, d_lo, (uint32_t)g.d_plane, SWd, 0, nullptr, nullptr, false, 0, t, TS);
       // T(x) halo: channels [ci_lo, ci_lo + ci_n) of each parity plane
       for (int q = 0; q < g.nq; ++q) {
-        if (g.Va == 4) stage_rows<4>(p.x, p.Cin, ci_lo, ci_n, g.Lpad, tab, g.nq, q, st + a_off, a_lo, (uint32_t)g.a_plane, SWa,
+        if (g.Va == 4) stage_rows8<4>(p.x, p.Cin, ci_lo, ci_n, g.Lpad, tab, g.nq, q, st + a_off, a_lo, (uint32_t)g.a_plane, SWa,
                                      (uint32_t)(q * g.CI * 2), s_sc, s_sh, p.in_scale != nullptr, p.in_relu, t, TS);
-        else stage_rows<2>(p.x, p.Cin, ci_lo, ci_n, g.Lpad, tab, g.nq, q, st + a_off, a_lo, (uint32_t)g.a_plane, SWa,
+        else stage_rows8<2>(p.x, p.Cin, ci_lo, ci_n, g.Lpad, tab, g.nq, q, st + a_off, a_lo, (uint32_t)g.a_plane, SWa,
                            (uint32_t)(q * g.CI * 2), s_sc, s_sh, p.in_scale != nullptr, p.in_relu, t, TS);
       }
       fence_proxy_async();

@@ -794,17 +794,12 @@ class Engine:
         G2.consumers += 3
         # --- dense
         kept = K.empty(B)
-        A, D = K.empty(B * S, 128), K.empty(B * S, 128)
-        inv_a, inv_d = K.empty(B * S), K.empty(B * S)
-        Ld = K.empty(B, S, S)
-        stat = K.empty(B, 2, S, 4)
+        stat = K.zeros(B, 2, S, 4)
         fin_d = K.zeros(8)
         p.f(K.dense_kept, self.depth_mask, B, self.R, h, kept)
-        p.f(K.gather_l2norm, G1.data, 0, self.dense_idx, HW, S, B * S, 128, A, 128, inv_a)
-        p.f(K.gather_l2norm, G2.data, 0, self.dense_idx, HW, S, B * S, 128, D, 128, inv_d)
-        # L[b][i][j] = <d_i, a_j>/T
-        p.f(K.gemm, D, A, None, Ld, B, S, S, 128, 128, 1, 1, 128, S, S * 128, S * 128, S * S, 1.0 / T, 0)
-        p.f(K.dense_stats, Ld, self.dense_idx, kept, self.use_depth, B, S, h, stat, fin_d)
+        # one fused kernel: gather + L2-norm + S x S x 128 affinity (tcgen05) + soft-target statistics; L[b][i][j] = <d_i, a_j>/T
+        # stays on chip (the unfused chain gather_l2norm -> gemm -> dense_stats remains in the C-ABI and the kernel tests)
+        p.f(K.dense_affinity_fwd, G1.data, G2.data, self.dense_idx, kept, self.use_depth, B, S, h, 128, 1.0 / T, stat, fin_d)
         p.f(K.bn_apply, fin_d, None, None, None, None, None, 0, self.losses[6:8], 1, 2)
         p.f(K.bn_apply, fin_d[2:4], None, None, None, None, None, 0, self.accs[6:8], 1, 2)
         # --- joints: F rows [0,BJ) rgb pixels, [BJ,2BJ) depth pixels (also the SCL feature matrix)
@@ -832,7 +827,7 @@ class Engine:
         p.f(K.gemm, Fm, Fm, None, Z, 1, N, N, 128, 128, 1, 1, 128, N, 0, 0, 0, 1.0 / T, 0)
         p.f(K.scl_stats, Z, B, J, None, self.use_depth, rowstat, fin_s)
         p.f(K.bn_apply, fin_s, None, None, None, None, None, 0, self.losses[10:11], 1, 1)
-        self.stage2_debug = dict(Ld=Ld, Lr=Lr, Ldj=Ldj, Z=Z, fin_d=fin_d, fin_j=fin_j, fin_s=fin_s, kept=kept, pixj=pixj)
+        self.stage2_debug = dict(stat=stat, Lr=Lr, Ldj=Ldj, Z=Z, fin_d=fin_d, fin_j=fin_j, fin_s=fin_s, kept=kept, pixj=pixj)
 
         def backward():
             iT = 1.0 / T
@@ -853,13 +848,8 @@ class Engine:
             p.b(K.gather_l2norm_bwd, dFd, 128, Fd, 128, inv_f[B * J:], pixj, HW, J, B * J, 128, g2, 0, 1)
             gs, acc = self._slot_grad(self.feat3_slot, (B, J, 128))
             p.b(K.gather_l2norm_bwd, dSk, 128, Sk, 128, inv_s, None, 0, 1, B * J, 128, gs, 128, acc)
-            # dense: dL in place; dD = iT * dL A ; dA = iT * dL^T D
-            dA, dD = K.empty(B * S, 128), K.empty(B * S, 128)
-            p.b(K.dense_grad, Ld, self.dense_idx, stat, kept, fin_d, B, S, h, 1.0)
-            p.b(K.gemm, Ld, A, None, dD, B, S, 128, S, S, 1, 128, 1, 128, S * S, S * 128, S * 128, iT, 0)
-            p.b(K.gemm, Ld, D, None, dA, B, S, 128, S, 1, S, 128, 1, 128, S * S, S * 128, S * 128, iT, 0)
-            p.b(K.gather_l2norm_bwd, dA, 128, A, 128, inv_a, self.dense_idx, HW, S, B * S, 128, g1, 0, 1)
-            p.b(K.gather_l2norm_bwd, dD, 128, D, 128, inv_d, self.dense_idx, HW, S, B * S, 128, g2, 0, 1)
+            # dense: affinity recomputed on chip, logit gradient -> second MMA -> L2-norm backward -> atomic scatter
+            p.b(K.dense_affinity_bwd, G1.data, G2.data, self.dense_idx, stat, kept, fin_d, B, S, h, 128, iT, 1.0, g1, g2)
 
         p.on_backward(backward)
 

@@ -449,6 +449,52 @@ class TorchKernels:
         Lb.copy_(g)
         return 0
 
+    def dense_finish(self, stat, kept, use_depth, B, S, fin):
+        st = stat.reshape(B, 2, S, 4)
+        k = kept.reshape(-1)[:B]
+        nk = k.sum()
+        nd = (use_depth != 0).sum() if use_depth is not None else torch.tensor(B)
+        on = bool(nd > 0) and bool(nk > 0)
+        inv = 1.0 / (nk * S) if on else 0.0
+        per = st[..., 0] - st[..., 2] / st[..., 1]
+        per = torch.where(k.view(B, 1, 1) != 0, per, torch.zeros_like(per))
+        hit = torch.where(k.view(B, 1, 1) != 0, st[..., 3], torch.zeros_like(per))
+        fin[0], fin[1] = per[:, 0].sum() * inv, per[:, 1].sum() * inv
+        fin[2], fin[3] = hit[:, 0].sum() * inv, hit[:, 1].sum() * inv
+        fin[4] = nk if on else 0.0
+        return 0
+
+    # fused form (dense_affinity.cu) = gather_l2norm x2 -> affinity GEMM -> dense_stats / dense_grad -> GEMMs -> scatter
+    def dense_affinity_fwd(self, G1, G2, pix, kept, use_depth, B, S, h, dim, inv_T, stat, fin):
+        HW = h * h
+        A, D = torch.empty(B * S, dim, dtype=G1.dtype, device=G1.device), torch.empty(B * S, dim, dtype=G1.dtype, device=G1.device)
+        self.gather_l2norm(G1, 0, pix, HW, S, B * S, dim, A, dim, None)
+        self.gather_l2norm(G2, 0, pix, HW, S, B * S, dim, D, dim, None)
+        L = torch.matmul(D.reshape(B, S, dim), A.reshape(B, S, dim).transpose(1, 2)) * inv_T
+        k = kept.reshape(-1)[:B]
+        st = torch.zeros(B, 2, S, 4, dtype=G1.dtype, device=G1.device)
+        self.dense_stats(L, pix, kept, use_depth, B, S, h, st, fin)
+        sv = stat.reshape(B, 2, S, 4)
+        sv[k != 0] = st[k != 0]          # the fused kernel skips dropped samples
+        return 0
+
+    def dense_affinity_bwd(self, G1, G2, pix, stat, kept, fin, B, S, h, dim, inv_T, gscale, dG1, dG2):
+        HW = h * h
+        mk = lambda *s: torch.empty(*s, dtype=G1.dtype, device=G1.device)      # noqa: E731
+        A, D, ia, idn = mk(B * S, dim), mk(B * S, dim), mk(B * S), mk(B * S)
+        self.gather_l2norm(G1, 0, pix, HW, S, B * S, dim, A, dim, ia)
+        self.gather_l2norm(G2, 0, pix, HW, S, B * S, dim, D, dim, idn)
+        A3, D3 = A.reshape(B, S, dim), D.reshape(B, S, dim)
+        L = torch.matmul(D3, A3.transpose(1, 2)) * inv_T
+        k = kept.reshape(-1)[:B]
+        st = torch.where(k.view(B, 1, 1, 1) != 0, stat.reshape(B, 2, S, 4), torch.ones_like(stat.reshape(B, 2, S, 4)))
+        self.dense_grad(L, pix, st, kept, fin, B, S, h, gscale)
+        dD = (torch.matmul(L, A3) * inv_T).reshape(B * S, dim)
+        dA = (torch.matmul(L.transpose(1, 2), D3) * inv_T).reshape(B * S, dim)
+        self.gather_l2norm_bwd(dA.contiguous(), dim, A, dim, ia, pix, HW, S, B * S, dim, dG1, 0, 1)
+        self.gather_l2norm_bwd(dD.contiguous(), dim, D, dim, idn, pix, HW, S, B * S, dim, dG2, 0, 1)
+        return 0
+
     def joint_stats(self, Lr, Ld, vis, use_depth, B, J, rs, lse, fin):
         r = rs.reshape(B, 2, 3)
         ls = lse.reshape(B, 2, J)

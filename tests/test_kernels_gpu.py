@@ -240,6 +240,47 @@ def test_gather_l2norm(KK):
          [10], tol=1e-4)
 
 
+@pytest.mark.parametrize("B,h,S", [(4, 16, 60), (3, 32, 400), (2, 8, 130), (5, 64, 400)])
+def test_dense_affinity_fused(KK, B, h, S):
+    """Fused tcgen05 dense-affinity kernels (gather + L2-norm + S x S x 128 affinity + soft-target statistics; backward by
+    recompute + second MMA + atomic scatter) against the unfused fp32 statement (contrast_trainer.py:684-723)."""
+    kc, kr = KK
+    g = torch.Generator().manual_seed(B + S)
+    G1 = torch.randn(B, h * h, 128, generator=g).to(DEV)
+    G2 = 0.5 * torch.randn(B, h * h, 128, generator=g).to(DEV) + 0.5 * G1
+    pix = torch.randint(0, h * h, (B, S), generator=g).to(DEV)           # with replacement: duplicates as in the reference
+    kept = (torch.rand(B, generator=g) < 0.7).float().to(DEV)
+    kept[0] = 1
+    use_depth = torch.ones(B, dtype=torch.int64, device=DEV)
+    iT = 1.0 / 0.07
+    out = []
+    for kk in (kc, kr):
+        stat, fin = torch.zeros(B, 2, S, 4, device=DEV), torch.zeros(8, device=DEV)
+        kk.dense_affinity_fwd(G1, G2, pix, kept, use_depth, B, S, h, 128, iT, stat, fin)
+        out.append((stat, fin))
+    torch.cuda.synchronize()
+    m = kept != 0
+    for i in range(3):
+        assert rel(out[0][0][m][..., i], out[1][0][m][..., i]) < 1e-5, i
+    assert float((out[0][0][m][..., 3] != out[1][0][m][..., 3]).float().mean()) < 0.01      # argmax near-ties
+    assert rel(out[0][1][:2], out[1][1][:2]) < 1e-5 and rel(out[0][1][2:5], out[1][1][2:5]) < 1e-2
+    stat, fin = out[1]
+    d = []
+    for kk in (kc, kr):
+        d1, d2 = torch.zeros_like(G1), torch.zeros_like(G2)
+        kk.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, iT, 1.0, d1, d2)
+        d.append((d1, d2))
+    torch.cuda.synchronize()
+    assert rel(d[0][0], d[1][0]) < 2e-4 and rel(d[0][1], d[1][1]) < 2e-4
+    # all depth off -> exact zeros, and a backward that adds nothing
+    stat, fin = torch.zeros(B, 2, S, 4, device=DEV), torch.ones(8, device=DEV)
+    kc.dense_affinity_fwd(G1, G2, pix, kept, torch.zeros_like(use_depth), B, S, h, 128, iT, stat, fin)
+    assert float(fin[:5].abs().sum()) == 0.0
+    d1, d2 = torch.zeros_like(G1), torch.zeros_like(G2)
+    kc.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, iT, 1.0, d1, d2)
+    assert float(d1.abs().sum() + d2.abs().sum()) == 0.0
+
+
 def test_stage2_loss_kernels(KK):
     kc, kr = KK
     B, J, h, S, R = 4, 13, 16, 60, 64
