@@ -22,7 +22,8 @@
 namespace {
 
 constexpr int DA_C = 128;          // feature channels
-constexpr int DA_THREADS = 256;
+constexpr int DA_THREADS = 512;         // 16 warps: 4 per TMEM lane quarter
+constexpr int DA_PARTS = DA_THREADS / 128;  // column parts of the epilogue (one per warp of a lane quarter)
 constexpr int DA_HDR = 1024;
 
 struct DaGeo {
@@ -42,8 +43,8 @@ DaGeo da_geo(int S, int h, bool bwd) {
   g.lbo_x = 128 * 16 + 16;
   g.lbo_y = (uint32_t)g.NC * 16 + 16;
   uint32_t o = DA_HDR;
-  g.off_tab = o; o += (uint32_t)g.Spad * 4 * 4;                  // cy, cx, lse_other, zinv_other
-  g.off_red = o; o += 128 * 8 * 4;
+  g.off_tab = o; o += (uint32_t)g.Spad * 5 * 4;                  // cy, cx, lse_other, zinv_other, pixel offset
+  g.off_red = o; o += DA_PARTS * 128 * 8 * 4;
   o = (o + 127) / 128 * 128;
   g.off_x = o; o += 2 * 16 * g.lbo_x;                            // X hi | X lo   (also the fp32 staging of the scatter)
   g.off_y = o; o += 2 * 16 * g.lbo_y;                            // Y hi | Y lo
@@ -77,36 +78,33 @@ __device__ __forceinline__ uint32_t da_idesc(int N, int b_mn) {
 }
 
 // Stage rows [first, first + nrows) of one sample (row r valid if first + r < last): gather 128 channels from the
-// channels-last map, L2-normalise (F.normalize, eps 1e-12), split into bf16 hi / lo, write both K-major slabs
-// ([channel/8][row][8 channels], chunk stride lbo).  One warp per row, 4 rows in flight per warp.
-__device__ __forceinline__ void da_stage(const float* __restrict__ map_b, const long long* __restrict__ pix_b, int first, int last,
+// channels-last map (s_off[row] = element offset of the sampled pixel), L2-normalise (F.normalize, eps 1e-12), split into
+// bf16 hi / lo, write both K-major slabs ([channel/8][row][8 channels], chunk stride lbo).  One warp per row (512 B
+// coalesced), 8 rows in flight per warp: the gather is pure latency.
+__device__ __forceinline__ void da_stage(const float* __restrict__ map_b, const int* __restrict__ s_off, int first, int last,
                                          int nrows, uint8_t* hi, uint8_t* lo, uint32_t lbo, int warp, int lane) {
-  for (int r0 = warp * 4; r0 < nrows; r0 += (DA_THREADS / 32) * 4) {
-    float4 v[4];
+  constexpr int U = 8;
+  for (int r0 = warp * U; r0 < nrows; r0 += (DA_THREADS / 32) * U) {
+    float4 v[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int r = r0 + u, gr = first + r;
       v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < nrows && gr < last) v[u] = __ldg(reinterpret_cast<const float4*>(map_b + pix_b[gr] * DA_C + 4 * lane));
+      if (r < nrows && gr < last) v[u] = __ldg(reinterpret_cast<const float4*>(map_b + s_off[gr] + 4 * lane));
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int r = r0 + u;
       if (r >= nrows) break;
       const float ss = warp_sum(v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w);
       const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
       const float x0 = v[u].x * inv, x1 = v[u].y * inv, x2 = v[u].z * inv, x3 = v[u].w * inv;
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1), h2 = __float2bfloat16_rn(x2),
-                          h3 = __float2bfloat16_rn(x3);
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1)),
-                          l2 = __float2bfloat16_rn(x2 - __bfloat162float(h2)), l3 = __float2bfloat16_rn(x3 - __bfloat162float(h3));
+      uint32_t h01, l01, h23, l23;
+      split2(x0, x1, h01, l01);
+      split2(x2, x3, h23, l23);
       const uint32_t off = (uint32_t)(lane >> 1) * lbo + (uint32_t)r * 16 + (uint32_t)(lane & 1) * 8;
-      *reinterpret_cast<uint2*>(hi + off) =
-          make_uint2((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16),
-                     (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16));
-      *reinterpret_cast<uint2*>(lo + off) =
-          make_uint2((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16),
-                     (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16));
+      *reinterpret_cast<uint2*>(hi + off) = make_uint2(h01, h23);
+      *reinterpret_cast<uint2*>(lo + off) = make_uint2(l01, l23);
     }
   }
 }
@@ -137,6 +135,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
   float* s_cx = s_cy + g.Spad;
   float* s_lse_o = s_cx + g.Spad;
   float* s_zinv_o = s_lse_o + g.Spad;
+  int* s_off = reinterpret_cast<int*>(s_zinv_o + g.Spad);
   float* s_red = reinterpret_cast<float*>(smem + g.off_red);
   uint8_t* Xhi = smem + g.off_x;
   uint8_t* Xlo = Xhi + 16 * g.lbo_x;
@@ -157,21 +156,22 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
     const long long px = q < S ? pix_b[q] : 0;
     s_cy[q] = (float)(px / g.h);
     s_cx[q] = (float)(px % g.h);
+    s_off[q] = (int)px * DA_C;
     if (BWD) {
       const float* so = p.stat + (((long)b * 2 + (1 - side)) * S + (q < S ? q : 0)) * 4;
       s_lse_o[q] = so[0];
       s_zinv_o[q] = 1.f / so[1];
     }
   }
-  da_stage(Xmap, pix_b, row0, row_end, 128, Xhi, Xlo, g.lbo_x, warp, lane);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  da_stage(Xmap, s_off, row0, row_end, 128, Xhi, Xlo, g.lbo_x, warp, lane);
   const uint32_t tmem = *tmem_ptr;
   const uint32_t tP = tmem, tdX = tmem + 128;
 
-  // this thread's strip row (TMEM lane) and column half
-  const int qtr = warp & 3, half = warp >> 2;
+  // this thread's strip row (TMEM lane) and column part (8-column groups part, part + DA_PARTS, ...)
+  const int qtr = warp & 3, part = warp >> 2;
   const int row = qtr * 32 + lane;
   const int grow = row0 + row;
   const bool row_ok = grow < row_end;
@@ -184,12 +184,11 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
   }
   float mx = -INFINITY, se = 0.f, Z = 0.f, wl = 0.f;
   int am = 0;
-  const int hc = g.NC / 2;                       // columns per half (multiple of 8)
   const uint32_t idesc1 = da_idesc(g.NC, 0), idesc2 = da_idesc(128, 1);
   uint32_t ph1 = 0, ph2 = 0;
 
   for (int c = 0; c < g.nchunks; ++c) {
-    da_stage(Ymap, pix_b, c * g.NC, S, g.NC, Yhi, Ylo, g.lbo_y, warp, lane);
+    da_stage(Ymap, s_off, c * g.NC, S, g.NC, Yhi, Ylo, g.lbo_y, warp, lane);
     fence_proxy_async();
     __syncthreads();
     if (warp == 0) {
@@ -212,8 +211,8 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
     ph1 ^= 1;
     tc_fence_after();
 
-    // ---- epilogue over this thread's half of the chunk columns
-    for (int c0 = half * hc; c0 < (half + 1) * hc; c0 += 8) {
+    // ---- epilogue over this thread's 8-column groups of the chunk
+    for (int c0 = part * 8; c0 < g.NC; c0 += DA_PARTS * 8) {
       float v[8];
       tmem_ld8(tP + ((uint32_t)(qtr * 32) << 16) + (uint32_t)c0, v);
       const int q0 = c * g.NC + c0;
@@ -286,58 +285,65 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
   }
 
   if (!BWD) {
-    // ---- combine the two column halves of every row; first maximal index wins (torch.argmax)
-    if (half == 1) {
-      float* r = s_red + row * 8;
+    // ---- combine the column parts of every row; the first maximal index wins (torch.argmax)
+    if (part > 0) {
+      float* r = s_red + ((part - 1) * 128 + row) * 8;
       r[0] = mx; r[1] = se; r[2] = Z; r[3] = wl; r[4] = __int_as_float(am);
     }
     __syncthreads();
-    if (half == 0 && row_ok) {
-      const float* r = s_red + row * 8;
-      const float mx2 = r[0], se2 = r[1];
-      const int am2 = __float_as_int(r[4]);
-      const float m = fmaxf(mx, mx2);
-      const float s = se * __expf(mx - m) + se2 * __expf(mx2 - m);
-      int a = am;
-      if (mx2 > mx || (mx2 == mx && am2 < am)) a = am2;
+    if (part == 0 && row_ok) {
+#pragma unroll
+      for (int pp = 0; pp < DA_PARTS - 1; ++pp) {
+        const float* r = s_red + (pp * 128 + row) * 8;
+        const float mx2 = r[0], se2 = r[1];
+        const int am2 = __float_as_int(r[4]);
+        const float m = fmaxf(mx, mx2);
+        se = se * __expf(mx - m) + se2 * __expf(mx2 - m);
+        if (mx2 > mx || (mx2 == mx && am2 < am)) am = am2;
+        mx = m;
+        Z += r[2];
+        wl += r[3];
+      }
       float* o = p.stat + (((long)b * 2 + side) * S + grow) * 4;
-      o[0] = m + logf(s);
-      o[1] = Z + r[2];
-      o[2] = wl + r[3];
-      o[3] = (a == grow) ? 1.f : 0.f;
+      o[0] = mx + logf(se);
+      o[1] = Z;
+      o[2] = wl;
+      o[3] = (am == grow) ? 1.f : 0.f;
     }
   } else {
     // ---- L2-norm backward of the strip rows: dx = inv_T * (dXn - xn <dXn, xn>) / |x|, then atomic scatter
-    const float* xrow = Xmap + (row_ok ? pix_b[grow] : 0) * DA_C + half * 64;
+    constexpr int CW = DA_C / DA_PARTS;                 // channels per thread
+    const float* xrow = Xmap + s_off[row_ok ? grow : 0] + part * CW;
     float dot = 0.f, ss = 0.f;
-    for (int c0 = 0; c0 < 64; c0 += 8) {
+    for (int c0 = 0; c0 < CW; c0 += 8) {
       float v[8];
-      tmem_ld8(tdX + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(half * 64 + c0), v);
+      tmem_ld8(tdX + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(part * CW + c0), v);
       const float4 xa = __ldg(reinterpret_cast<const float4*>(xrow + c0)), xb = __ldg(reinterpret_cast<const float4*>(xrow + c0 + 4));
       const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) { dot = fmaf(v[i], x[i], dot); ss = fmaf(x[i], x[i], ss); }
     }
-    s_red[(half * 128 + row) * 2 + 0] = dot;
-    s_red[(half * 128 + row) * 2 + 1] = ss;
+    s_red[(part * 128 + row) * 2 + 0] = dot;
+    s_red[(part * 128 + row) * 2 + 1] = ss;
     __syncthreads();                                  // also: all MMAs are complete, the X slabs are free
-    dot = s_red[row * 2] + s_red[(128 + row) * 2];
-    ss = s_red[row * 2 + 1] + s_red[(128 + row) * 2 + 1];
+    dot = 0.f; ss = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < DA_PARTS; ++pp) { dot += s_red[(pp * 128 + row) * 2]; ss += s_red[(pp * 128 + row) * 2 + 1]; }
     const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
     const float dotn = dot * inv;                     // <dXn, xn>
     float* stage = reinterpret_cast<float*>(Xhi);     // [128][129] fp32
-    for (int c0 = 0; c0 < 64; c0 += 8) {
+    for (int c0 = 0; c0 < CW; c0 += 8) {
       float v[8];
-      tmem_ld8(tdX + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(half * 64 + c0), v);
+      tmem_ld8(tdX + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(part * CW + c0), v);
       const float4 xa = __ldg(reinterpret_cast<const float4*>(xrow + c0)), xb = __ldg(reinterpret_cast<const float4*>(xrow + c0 + 4));
       const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) stage[row * 129 + half * 64 + c0 + i] = p.inv_T * (v[i] - x[i] * inv * dotn) * inv;
+      for (int i = 0; i < 8; ++i) stage[row * 129 + part * CW + c0 + i] = p.inv_T * (v[i] - x[i] * inv * dotn) * inv;
     }
     __syncthreads();
     float* dmap = (side == 0 ? p.dG1 : p.dG2) + (long)b * g.HW * DA_C;
     for (int r = warp; r < row_end - row0; r += DA_THREADS / 32) {
-      float* dst = dmap + pix_b[row0 + r] * DA_C;
+      float* dst = dmap + s_off[row0 + r];
 #pragma unroll
       for (int i = 0; i < 4; ++i) atomicAdd(dst + lane + 32 * i, stage[r * 129 + lane + 32 * i]);
     }

@@ -356,7 +356,7 @@ int hcm_dense_stats(const float* L, const long long* pix, const float* kept, con
 int hcm_dense_finish(const float* stat, const float* kept, const long long* use_depth, int B, int S, float* fin,
                      cudaStream_t stream) {
   HCM_CHECK_ARG(stat && kept && fin, "dense_finish: null pointer");
-  dense_finish_kernel<<<1, 256, 0, stream>>>(stat, kept, use_depth, B, S, fin);
+  dense_finish_kernel<<<1, 1024, 0, stream>>>(stat, kept, use_depth, B, S, fin);
   HCM_LAUNCH_CHECK("dense_finish");
   return HCM_OK;
 }

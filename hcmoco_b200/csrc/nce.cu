@@ -156,7 +156,7 @@ __global__ void nce_finish_kernel(const float* __restrict__ lse, const float* __
 }
 
 // grid (ceil(K1/ROWS_PER_CTA), B); df [B][3*128] += (atomics over the K-slices)
-__global__ void __launch_bounds__(NCE_THREADS) nce_bwd_kernel(const NceArgs a, const float* __restrict__ logits,
+__global__ void __launch_bounds__(NCE_THREADS, 2) nce_bwd_kernel(const NceArgs a, const float* __restrict__ logits,
                                                               const float* __restrict__ lse, const float* __restrict__ coef,
                                                               float gscale, float* df, long lddf) {
   __shared__ float4 sacc[NCE_THREADS / 32][3][4][8];

@@ -75,6 +75,22 @@ __global__ void fuse_sum_kernel(const FuseParams p) {
 }
 
 // out[b,Y,X,c] (+)= sum over high-res (h,w) of weight(h->Y)*weight(w->X) * g[b,h,w,c]
+// f = 2^k, align_corners=False: s = (dst + 0.5)/f - 0.5 = num/(2f) with num = max(2*dst + 1 - f, 0), so i0 = num >> (k+1) and
+// l1 = (num & (2f-1)) / 2f are exact integer expressions of the same fp32 values src_index() produces.  Only the 2f rows
+// (columns) [f*Y - f/2, f*Y + 3f/2) can have i0 or i1 equal to Y.
+__device__ __forceinline__ float adj_weight(int dst, int k, int in_size, int target) {
+  const int f2 = 2 << k;
+  int num = 2 * dst + 1 - (1 << k);
+  num = max(num, 0);
+  const int i0 = num >> (k + 1);
+  const float l1 = (float)(num & (f2 - 1)) / (float)f2;
+  const int i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  float w = 0.f;
+  if (i0 == target) w += 1.f - l1;
+  if (i1 == target) w += l1;
+  return w;
+}
+
 __global__ void upsample_adjoint_kernel(const float* __restrict__ g, float* out, int accumulate, int B, int H, int W, int C,
                                         int log2f) {
   const int f = 1 << log2f;
@@ -88,29 +104,14 @@ __global__ void upsample_adjoint_kernel(const float* __restrict__ g, float* out,
     pix /= Ws;
     const int Y = (int)(pix % Hs);
     const int b = (int)(pix / Hs);
-    // candidate high-res rows: those whose y0 or y1 can equal Y
-    const int hlo = max(0, f * Y - f), hhi = min(H - 1, f * Y + 2 * f - 1);
-    const int wlo = max(0, f * X - f), whi = min(W - 1, f * X + 2 * f - 1);
+    const int hlo = max(0, f * Y - f / 2), hhi = min(H - 1, f * Y + f + f / 2 - 1);
+    const int wlo = max(0, f * X - f / 2), whi = min(W - 1, f * X + f + f / 2 - 1);
     float acc = 0.f;
     for (int h = hlo; h <= hhi; ++h) {
-      int y0, y1;
-      float ly;
-      src_index(h, f, Hs, y0, y1, ly);
-      float wy = 0.f;
-      if (y0 == Y) wy += 1.f - ly;
-      if (y1 == Y) wy += ly;
-      if (wy == 0.f) continue;
+      const float wy = adj_weight(h, log2f, Hs, Y);
       const float* row = g + ((long)(b * H + h) * W) * C + c;
       float racc = 0.f;
-      for (int w = wlo; w <= whi; ++w) {
-        int x0, x1;
-        float lx;
-        src_index(w, f, Ws, x0, x1, lx);
-        float wx = 0.f;
-        if (x0 == X) wx += 1.f - lx;
-        if (x1 == X) wx += lx;
-        if (wx != 0.f) racc = fmaf(wx, row[(long)w * C], racc);
-      }
+      for (int w = wlo; w <= whi; ++w) racc = fmaf(adj_weight(w, log2f, Ws, X), __ldg(row + (long)w * C), racc);
       acc = fmaf(wy, racc, acc);
     }
     out[e] = accumulate ? out[e] + acc : acc;

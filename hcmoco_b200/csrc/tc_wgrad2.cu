@@ -186,6 +186,10 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
     const uint64_t a_t = mn_desc(0, SWa, concat ? SWa : (uint32_t)g.a_plane);
     const uint32_t idesc = instr_desc(concat ? 3 * g.CI : g.CI, 1);
     const int nmma = concat ? 3 : g.taps;                       // MMAs per K step and pass
+    // One staged dy plane (Cout block <= SWd/2 channels): the M=128 operand read through the dy_hi descriptor covers the dy_lo
+    // plane as its next MN block, so accumulator rows [SWd/2, SWd/2 + co_n) already hold dy_lo*(a_hi + a_lo).  The third
+    // MMA (dy_lo*a_hi) is then redundant: two MMAs per step, and the epilogue folds the two row blocks.
+    const bool fold = (g.d_blocks == 1);
     uint32_t* tap_boff = reinterpret_cast<uint32_t*>(smem + 3072);  // byte offset of the B operand / TMEM column per MMA
     uint32_t* tap_col = tap_boff + 16;
     for (int m = lane; m < 9; m += 32) {
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
           if (elect_one()) {
             umma_bf16(dcol, dyh, ah, idesc, acc);
             umma_bf16(dcol, dyh, al, idesc, 1u);
-            umma_bf16(dcol, dyl, ah, idesc, 1u);
+            if (!fold) umma_bf16(dcol, dyl, ah, idesc, 1u);
           }
         }
       }
@@ -265,8 +269,12 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
     mbar_wait(BAR(8), 0);
     tc_fence_after();
     const int q = warp & 3;
-    const int co = co_lo + q * 32 + lane;
-    const bool rowok = (q * 32 + lane) < co_n && ntiles > 0;
+    const int m = q * 32 + lane, bw = (int)SWd / 2;
+    // accumulator row -> output channel: rows [0, co_n) are dy_hi products; with a single dy plane rows [bw, bw + co_n) are
+    // the dy_lo products of the same channels (see `fold` in the MMA warp)
+    const int cr = (m < co_n) ? m : ((g.d_blocks == 1 && m >= bw && m - bw < co_n) ? m - bw : -1);
+    const int co = co_lo + cr;
+    const bool rowok = cr >= 0 && ntiles > 0;
     for (int tap = 0; tap < g.taps; ++tap) {
       for (int c0 = 0; c0 < g.CI; c0 += 16) {
         float v[16];

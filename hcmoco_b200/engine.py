@@ -284,10 +284,11 @@ class Engine:
         p.mark_f(FORK)
         self.feat1 = self._hrnet("encoder1.", xs[0])
         p.tag = 1
+        # the skeleton encoder's launches are tiny (B*J rows): on the side stream they hide under encoder1's kernels
+        self.feat3 = self._sgcn("encoder3.", self.skel)
         self.feat2 = self._hrnet("encoder2.", xs[1])
         p.tag = 0
         p.mark_f(JOIN)
-        self.feat3 = self._sgcn("encoder3.", self.skel)
         self.f = K.empty(B, 384)
         self.df = K.zeros(B, 384)
         self._head("head1.0", self._pool(self.feat1), self.cm, 0)

@@ -118,7 +118,9 @@ def test_cuda_graph_replay_is_identical(K):
         b.set_batch(batch, nce, dense)
         b.step_graph()
         ra, rb = a.results(), b.results()
-        assert rel(rb["loss"], ra["loss"]) < 1e-5      # atomics (wgrad split-K, scatter) reorder fp32 sums
+        # the forward is deterministic (bit-identical on the first step); fp32 atomics in the backward (wgrad split-K,
+        # gather scatters) reorder sums, and the 1e-7 gradient differences grow through the SGD steps (B=3 batch-norm)
+        assert rel(rb["loss"], ra["loss"]) < (1e-7 if s == 0 else 1e-4), (s, float(ra["loss"]), float(rb["loss"]))
     assert rel(b.store.p, a.store.p) < 1e-3
 
 
