@@ -175,6 +175,43 @@ def run_reference(a):
     print(json.dumps(out), flush=True)
 
 
+def dense_affinity_roofline(K, hbm_peak, B=32, h=64, S=400, reps=20):
+    """Device time of hcm_dense_affinity_{fwd,bwd} alone on configs[2]'s per-GPU shape; algorithmic bytes =
+    2*S*128*4 gathered features per depth-bearing triplet."""
+    g = torch.Generator().manual_seed(7)
+    G1 = torch.randn(B, h * h, 128, generator=g).cuda()
+    G2 = torch.randn(B, h * h, 128, generator=g).cuda()
+    pix = torch.randint(0, h * h, (B, S), generator=g).cuda()
+    kept = torch.ones(B, device="cuda")
+    use_depth = torch.ones(B, dtype=torch.int64, device="cuda")
+    stat, fin = torch.zeros(B, 2, S, 4, device="cuda"), torch.zeros(8, device="cuda")
+    d1, d2 = torch.zeros_like(G1), torch.zeros_like(G2)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2: evict the maps between launches
+    out = {}
+    for name, fn in (("dense_affinity_fwd", lambda: K.dense_affinity_fwd(G1, G2, pix, kept, use_depth, B, S, h, 128, 1 / 0.07, stat, fin)),
+                     ("dense_affinity_bwd", lambda: K.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1 / 0.07, 1.0, d1, d2))):
+        fn()
+        ms = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        ms /= reps
+        nbytes = B * 2 * S * 128 * 4
+        flops = 2.0 * B * 2 * S * S * 128 * (1 if name.endswith("fwd") else 2)      # both L and L^T strips (+ dX = G*Y)
+        out[name] = {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": nbytes, "us_per_launch": ms * 1e3,
+                     "useful_tflops": flops / (ms * 1e-3) / 1e12,
+                     "shape": "B=%d depth-bearing triplets, %dx%d maps, S=%d, L2 flushed between launches" % (B, h, h, S),
+                     "note": "AI = S/4 = 100 FLOP/B (x2 for both softmax directions): the 3-pass split-bf16 contraction and the "
+                             "exp-heavy epilogue bound it, not HBM (DESIGN.md 3.2)"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------ engine arm
 def run_engine(a):
     import torch.distributed as dist
@@ -261,20 +298,62 @@ def run_engine(a):
     conv_names = ("conv2d", "tc_conv", "tc_wgrad", "tc_dgrad", "_run_packs", "tc_pack")   # conv kernels + their weight packing
     conv_ms = sum(v["ms"] for k, v in fam.items() if k.startswith(conv_names))
     tot_ms = sum(v["ms"] for v in fam.values())
-    dom = max(fam.items(), key=lambda kv: kv[1]["ms"])[0]
-    roof = {"kernel": "convolution family: tc_conv / tc_wgrad / tc_dgrad_s2 (tcgen05) + SIMT igemm leftovers + weight packing",
-            "bound": "tensor",
-            "achieved": conv_useful / (conv_ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
-            "frac": conv_useful / (conv_ms * 1e-3) / 1e12 / tc_peak, "traffic": None,
-            "peak_source": peak_src + ", bf16 dense sustained", "share_of_step": conv_ms / tot_ms,
-            "algorithmic_flops_per_step": conv_useful, "kernel_ms_per_step": conv_ms, "dominant_family": dom}
+    # ---- roofline of the DOMINANT KERNEL: the (kernel, shape) with the largest summed device time inside one real step
+    dom_shape, dom = max(step.detail.items(), key=lambda kv: kv[1]["ms"])
+    parts = dom_shape.split()                            # e.g. "tc_conv 64x64 18->18 k3 s1"
+    hh, ww = [int(v) for v in parts[1].split("x")]
+    cin, cout = [int(v) for v in parts[2].split("->")]
+    ks = int(parts[3][1:]) or 2
+    dom_us = 1e3 * dom["ms"] / dom["calls"]
+    dom_flops = 2.0 * a.batch * hh * ww * cin * cout * ks * ks
+    dom_bytes = 4.0 * a.batch * hh * ww * (cin + cout)                      # fp32 activations in + out (weights are KBs)
+    ridge = tc_peak * 1e3 / hbm_peak                                          # FLOP/B
+    hbm_bound = dom_flops / dom_bytes < ridge
+    ncu_traffic = {}                                                         # per-launch DRAM bytes from the committed ncu captures
+    try:
+        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+    tr = ncu_traffic.get("%s B=%d" % (dom_shape, a.batch))
+    roof = {"kernel": dom_shape + " (B=%d; %d launches per step)" % (a.batch, dom["calls"]),
+            "bound": "hbm" if hbm_bound else "tensor",
+            "achieved": (dom_bytes / (dom_us * 1e-6) / 1e9) if hbm_bound else dom_flops / (dom_us * 1e-6) / 1e12,
+            "peak": hbm_peak if hbm_bound else tc_peak, "unit": "GB/s" if hbm_bound else "TFLOP/s",
+            "traffic": None if tr is None else tr["dram_bytes"],
+            "traffic_source": None if tr is None else tr["source"],
+            "peak_source": peak_src + (", copy bandwidth" if hbm_bound else ", bf16 dense sustained"),
+            "arithmetic_intensity_flop_per_byte": dom_flops / dom_bytes, "ridge_flop_per_byte": ridge,
+            "algorithmic_bytes_per_launch": dom_bytes, "algorithmic_flops_per_launch": dom_flops,
+            "us_per_launch": dom_us, "share_of_step": dom["ms"] / tot_ms,
+            "useful_tflops": dom_flops / (dom_us * 1e-6) / 1e12}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    other = {"conv_family": {"kernel": "tc_conv / tc_wgrad / tc_dgrad_s2 (tcgen05) + SIMT stem + weight packing", "bound": "tensor",
+                             "achieved": conv_useful / (conv_ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
+                             "frac": conv_useful / (conv_ms * 1e-3) / 1e12 / tc_peak, "share_of_step": conv_ms / tot_ms,
+                             "algorithmic_flops_per_step": conv_useful, "kernel_ms_per_step": conv_ms,
+                             "note": "useful FLOPs only: the bf16 hi/lo split passes are not counted"}}
+    # north-star KPI kernel 1: the widest stage-4 conv (3x3, C4 -> C4 at R/32)
+    from hcmoco_b200 import layout as L
+    c4, r32 = L.WIDTHS[a.width][-1], a.res // 32
+    kpi = step.detail.get("tc_conv %dx%d %d->%d k3 s1" % (r32, r32, c4, c4))
+    if kpi:
+        us = 1e3 * kpi["ms"] / kpi["calls"]
+        fl = 2.0 * a.batch * r32 * r32 * c4 * c4 * 9
+        other["stage4_conv"] = {"kernel": "tc_conv %dx%d %d->%d k3 s1 (forward + data gradient launches)" % (r32, r32, c4, c4),
+                                "bound": "tensor", "achieved": fl / (us * 1e-6) / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
+                                "frac": fl / (us * 1e-6) / 1e12 / tc_peak, "us_per_launch": us,
+                                "algorithmic_flops_per_launch": fl}
     nce_bytes = 3 * (a.nce_k + 1) * 128 * 4 * a.batch
-    nce = {}
     for name in ("nce_logits", "nce_bwd"):
         if name in fam:
             g = nce_bytes / (fam[name]["ms"] * 1e-3) / 1e9
-            nce[name] = {"bound": "hbm", "achieved": g, "peak": hbm_peak, "unit": "GB/s", "frac": g / hbm_peak,
-                         "algorithmic_bytes": nce_bytes, "ms": fam[name]["ms"]}
+            tr = ncu_traffic.get("%s B=%d" % (name, a.batch))
+            other[name] = {"bound": "hbm", "achieved": g, "peak": hbm_peak, "unit": "GB/s", "frac": g / hbm_peak,
+                           "algorithmic_bytes": nce_bytes, "ms": fam[name]["ms"],
+                           "traffic": None if tr is None else tr["dram_bytes"]}
+    # north-star KPI kernel 2: the fused dense-affinity kernels on the second-stage per-GPU shape (B=32, 64x64 maps, S=400)
+    other.update(dense_affinity_roofline(K, hbm_peak))
+    nce = other
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",

@@ -38,13 +38,93 @@ __device__ __forceinline__ void vstore(float* p, const float (&v)[VEC]) {
   *reinterpret_cast<typename VecT<VEC>::T*>(p) = t;
 }
 
+struct FwdFin {      // forward finalize outputs / state (bn_finalize)
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var; long long* nbt;
+  float momentum, eps;
+  float* scale; float* shift; float* mean_out; float* invstd_out;
+};
+struct BwdFin {      // backward finalize (bn_bwd_finalize)
+  const float* gamma; const float* mean; const float* invstd;
+  float* dgamma; float* dbeta; float* k1; float* k2; float* k3;
+};
+
+// channel c from its fp64 sums s = sum y, q = sum y^2
+__device__ __forceinline__ void fwd_finalize_channel(const FwdFin& f, int c, double s, double q, double count) {
+  const double m = s / count;
+  double var = q / count - m * m;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)f.eps));
+  const float g = f.gamma ? f.gamma[c] : 1.f, b = f.beta ? f.beta[c] : 0.f;
+  f.scale[c] = g * is;
+  f.shift[c] = b - (float)m * g * is;
+  f.mean_out[c] = (float)m;
+  f.invstd_out[c] = is;
+  if (f.running_mean) {
+    const double unb = (count > 1.0) ? var * count / (count - 1.0) : var;
+    f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * (float)m;
+    f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unb;
+  }
+}
+// channel c from s = sum g, q = sum g*yhat: dgamma, dbeta and dy = k1*g + k2*y + k3
+__device__ __forceinline__ void bwd_finalize_channel(const BwdFin& f, int c, double s, double q, double count) {
+  const float g = f.gamma ? f.gamma[c] : 1.f;
+  const double is = f.invstd[c], mu = f.mean[c];
+  if (f.dgamma) f.dgamma[c] = (float)q;
+  if (f.dbeta) f.dbeta[c] = (float)s;
+  const double m1 = s / count, m2 = q / count;
+  const double a = (double)g * is;
+  f.k1[c] = (float)a;
+  f.k2[c] = (float)(-a * is * m2);
+  f.k3[c] = (float)(-a * m1 + a * is * mu * m2);
+}
+
+// Finalize inside the statistics kernel: the CTA that takes the last ticket reduces all partial rows (fp64, fixed order ->
+// deterministic) and writes the per-channel coefficients, saving a ~5 us kernel + its launch gap per BatchNorm.
+// Lanes run over channels (coalesced rows of `part`), warps over partial rows; 32 channels per round.
+template <class Fin, int MODE>
+__device__ __forceinline__ void finalize_in_cta(const float* part, int nparts, int C, double count, const Fin& f, double* s_acc) {
+  // thread t -> (channel c = t % C, row slice r = t / C of R = blockDim.x / C slices): consecutive threads read consecutive
+  // channels of a partial row (coalesced); 8 rows (16 loads) in flight per thread — the tail is pure L2 latency
+  const int t = threadIdx.x;
+  const int R = blockDim.x / C;                          // >= 1 (blockDim.x >= C for every launch plan)
+  const int c = t % C, r = t / C;
+  double s = 0.0, q = 0.0;
+  if (r < R) {
+    int i = r;
+    for (; i + 7 * R < nparts; i += 8 * R) {
+      float a[8], b[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a[k] = __ldcg(part + ((long)(i + k * R) * 2 + 0) * C + c);
+        b[k] = __ldcg(part + ((long)(i + k * R) * 2 + 1) * C + c);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s += (double)a[k]; q += (double)b[k]; }
+    }
+    for (; i < nparts; i += R) {
+      s += (double)__ldcg(part + ((long)i * 2 + 0) * C + c);
+      q += (double)__ldcg(part + ((long)i * 2 + 1) * C + c);
+    }
+  }
+  s_acc[t] = s;
+  s_acc[256 + t] = q;
+  __syncthreads();
+  if (t < C) {
+    double ss = 0.0, qq = 0.0;
+    for (int k = 0; k < R; ++k) { ss += s_acc[t + k * C]; qq += s_acc[256 + t + k * C]; }
+    if constexpr (MODE == 0) fwd_finalize_channel(f, t, ss, qq, count);
+    else bwd_finalize_channel(f, t, ss, qq, count);
+  }
+}
+
 // ---- column statistics: part[blk][0][c] = sum y, part[blk][1][c] = sum y^2 over the CTA's slice ----
 // MODE 0: plain (y).  MODE 1: backward sums (g, g*yhat) with g = dz * [mask > 0].
-template <int VEC, int MODE>
+template <int VEC, int MODE, class Fin>
 __global__ void colstat_kernel(const float* __restrict__ a, const float* __restrict__ y, const float* __restrict__ mask,
                                const float* __restrict__ mean, const float* __restrict__ invstd,
                                const float* __restrict__ msc, const float* __restrict__ msh, long total, int C,
-                               long per_cta, float* __restrict__ part) {
+                               long per_cta, float* part, unsigned int* counter, double count, const Fin fin) {
   __shared__ float s0[MAXT * 4], s1[MAXT * 4];
   const int t = threadIdx.x, nt = blockDim.x;
   const int cv = C / VEC;
@@ -98,6 +178,23 @@ __global__ void colstat_kernel(const float* __restrict__ a, const float* __restr
     part[((long)blockIdx.x * 2 + 0) * C + t] = r0;
     part[((long)blockIdx.x * 2 + 1) * C + t] = r1;
   }
+  if (counter) {
+    // last-ticket CTA finalizes (threadfence reduction pattern); it also re-arms the counter for the next launch
+    __shared__ int s_last;
+    __shared__ double s_acc[8 * 2 * 32];
+    __threadfence();
+    __syncthreads();
+    if (t == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      finalize_in_cta<Fin, MODE>(part, (int)gridDim.x, C, count, fin, s_acc);
+      if (t == 0) {
+        *counter = 0u;
+        if constexpr (MODE == 0) { if (fin.nbt) *fin.nbt += 1; }
+      }
+    }
+  }
 }
 
 // one CTA (128 threads) per channel: fp64 reduction of the partial rows, then the per-channel coefficients
@@ -111,41 +208,22 @@ __device__ __forceinline__ void block_sum2_d(double& s, double& q, double* red) 
 }
 
 __global__ void __launch_bounds__(128) bn_finalize_kernel(const float* __restrict__ part, int nparts, int C, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
-                                   float* scale, float* shift, float* mean_out, float* invstd_out) {
+                                                          const FwdFin f) {
   __shared__ double red[8];
   const int c = blockIdx.x;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && f.nbt) *f.nbt += 1;
   double s = 0.0, q = 0.0;
   for (int i = threadIdx.x; i < nparts; i += 128) {
     s += (double)part[((long)i * 2 + 0) * C + c];
     q += (double)part[((long)i * 2 + 1) * C + c];
   }
   block_sum2_d(s, q, red);
-  if (threadIdx.x == 0) {
-    const double m = s / count;
-    double var = q / count - m * m;
-    if (var < 0.0) var = 0.0;
-    const float is = (float)(1.0 / sqrt(var + (double)eps));
-    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
-    scale[c] = g * is;
-    shift[c] = b - (float)m * g * is;
-    mean_out[c] = (float)m;
-    invstd_out[c] = is;
-    if (running_mean) {
-      const double unb = (count > 1.0) ? var * count / (count - 1.0) : var;
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
-    }
-  }
+  if (threadIdx.x == 0) fwd_finalize_channel(f, c, s, q, count);
 }
 
 // backward finalize: dgamma, dbeta and dy = k1*g + k2*y + k3
 __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, double count,
-                                       const float* __restrict__ gamma, const float* __restrict__ mean,
-                                       const float* __restrict__ invstd, float* dgamma, float* dbeta, float* k1, float* k2,
-                                       float* k3) {
+                                                              const BwdFin f) {
   __shared__ double red[8];
   const int c = blockIdx.x;
   double s = 0.0, q = 0.0;
@@ -154,17 +232,7 @@ __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const float* __res
     q += (double)part[((long)i * 2 + 1) * C + c];
   }
   block_sum2_d(s, q, red);
-  if (threadIdx.x == 0) {
-    const float g = gamma ? gamma[c] : 1.f;
-    const double is = invstd[c], mu = mean[c];
-    if (dgamma) dgamma[c] = (float)q;
-    if (dbeta) dbeta[c] = (float)s;
-    const double m1 = s / count, m2 = q / count;
-    const double a = (double)g * is;
-    k1[c] = (float)a;
-    k2[c] = (float)(-a * is * m2);
-    k3[c] = (float)(-a * m1 + a * is * mu * m2);
-  }
+  if (threadIdx.x == 0) bwd_finalize_channel(f, c, s, q, count);
 }
 
 // z = act(y*scale + shift + (res*res_scale + res_shift))
@@ -280,6 +348,19 @@ inline void colstat_plan(long total, int C, int* vec, int* threads, int* nparts,
   *nparts = (int)((total + *per_cta - 1) / *per_cta);
 }
 
+template <int MODE, class Fin>
+int launch_colstat(const float* a, const float* y, const float* mask, const float* mean, const float* invstd, const float* msc,
+                   const float* msh, long P, int C, float* part, unsigned int* counter, const Fin& fin, cudaStream_t stream) {
+  int vec, threads, nparts;
+  long per;
+  const long total = P * C;
+  colstat_plan(total, C, &vec, &threads, &nparts, &per);
+  if (vec == 4) colstat_kernel<4, MODE, Fin><<<nparts, threads, 0, stream>>>(a, y, mask, mean, invstd, msc, msh, total, C, per, part, counter, (double)P, fin);
+  else if (vec == 2) colstat_kernel<2, MODE, Fin><<<nparts, threads, 0, stream>>>(a, y, mask, mean, invstd, msc, msh, total, C, per, part, counter, (double)P, fin);
+  else colstat_kernel<1, MODE, Fin><<<nparts, threads, 0, stream>>>(a, y, mask, mean, invstd, msc, msh, total, C, per, part, counter, (double)P, fin);
+  return HCM_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -294,13 +375,7 @@ int hcm_colstat_rows(long P, int C) {
 // part [hcm_colstat_rows][2][C]: per-CTA sums of y and y^2
 int hcm_bn_stats(const float* y, long P, int C, float* part, cudaStream_t stream) {
   HCM_CHECK_ARG(y && part && C >= 1 && C <= 256, "bn_stats: bad args (C=%d)", C);
-  int vec, threads, nparts;
-  long per;
-  const long total = P * C;
-  colstat_plan(total, C, &vec, &threads, &nparts, &per);
-  if (vec == 4) colstat_kernel<4, 0><<<nparts, threads, 0, stream>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, total, C, per, part);
-  else if (vec == 2) colstat_kernel<2, 0><<<nparts, threads, 0, stream>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, total, C, per, part);
-  else colstat_kernel<1, 0><<<nparts, threads, 0, stream>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, total, C, per, part);
+  launch_colstat<0>(y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, P, C, part, nullptr, FwdFin{}, stream);
   HCM_LAUNCH_CHECK("bn_stats");
   return HCM_OK;
 }
@@ -309,10 +384,23 @@ int hcm_bn_finalize(const float* part, int nparts, int C, long count, const floa
                     float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                     float* scale, float* shift, float* mean, float* invstd, cudaStream_t stream) {
   HCM_CHECK_ARG(part && scale && shift && mean && invstd && nparts >= 1, "bn_finalize: bad args");
-  bn_finalize_kernel<<<C, 128, 0, stream>>>(part, nparts, C, (double)count, gamma, beta, running_mean,
-                                                         running_var, num_batches_tracked, momentum, eps, scale, shift,
-                                                         mean, invstd);
+  const FwdFin f = {gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift, mean, invstd};
+  bn_finalize_kernel<<<C, 128, 0, stream>>>(part, nparts, C, (double)count, f);
   HCM_LAUNCH_CHECK("bn_finalize");
+  return HCM_OK;
+}
+
+// hcm_bn_stats + hcm_bn_finalize in ONE launch (count = P): the last CTA to finish reduces the partial rows.
+// `counter` is one zero-initialised uint32 owned by the caller (per stream); the kernel leaves it at zero.
+int hcm_bn_stats_finalize(const float* y, long P, int C, float* part, unsigned int* counter, const float* gamma,
+                          const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
+                          float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
+                          cudaStream_t stream) {
+  HCM_CHECK_ARG(y && part && counter && scale && shift && mean && invstd && C >= 1 && C <= 256,
+                "bn_stats_finalize: bad args (C=%d)", C);
+  const FwdFin f = {gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift, mean, invstd};
+  launch_colstat<0>(y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, P, C, part, counter, f, stream);
+  HCM_LAUNCH_CHECK("bn_stats_finalize");
   return HCM_OK;
 }
 
@@ -334,13 +422,7 @@ int hcm_bn_bwd_reduce(const float* dz, const float* mask, const float* mask_scal
                       const float* y, const float* mean, const float* invstd, long P, int C, float* part,
                       cudaStream_t stream) {
   HCM_CHECK_ARG(dz && y && mean && invstd && part && C >= 1 && C <= 256, "bn_bwd_reduce: bad args (C=%d)", C);
-  int vec, threads, nparts;
-  long per;
-  const long total = P * C;
-  colstat_plan(total, C, &vec, &threads, &nparts, &per);
-  if (vec == 4) colstat_kernel<4, 1><<<nparts, threads, 0, stream>>>(dz, y, mask, mean, invstd, mask_scale, mask_shift, total, C, per, part);
-  else if (vec == 2) colstat_kernel<2, 1><<<nparts, threads, 0, stream>>>(dz, y, mask, mean, invstd, mask_scale, mask_shift, total, C, per, part);
-  else colstat_kernel<1, 1><<<nparts, threads, 0, stream>>>(dz, y, mask, mean, invstd, mask_scale, mask_shift, total, C, per, part);
+  launch_colstat<1>(dz, y, mask, mean, invstd, mask_scale, mask_shift, P, C, part, nullptr, BwdFin{}, stream);
   HCM_LAUNCH_CHECK("bn_bwd_reduce");
   return HCM_OK;
 }
@@ -349,9 +431,22 @@ int hcm_bn_bwd_finalize(const float* part, int nparts, int C, long count, const 
                         const float* invstd, float* dgamma, float* dbeta, float* k1, float* k2, float* k3,
                         cudaStream_t stream) {
   HCM_CHECK_ARG(part && mean && invstd && k1 && k2 && k3, "bn_bwd_finalize: bad args");
-  bn_bwd_finalize_kernel<<<C, 128, 0, stream>>>(part, nparts, C, (double)count, gamma, mean, invstd, dgamma,
-                                                             dbeta, k1, k2, k3);
+  const BwdFin f = {gamma, mean, invstd, dgamma, dbeta, k1, k2, k3};
+  bn_bwd_finalize_kernel<<<C, 128, 0, stream>>>(part, nparts, C, (double)count, f);
   HCM_LAUNCH_CHECK("bn_bwd_finalize");
+  return HCM_OK;
+}
+
+// hcm_bn_bwd_reduce + hcm_bn_bwd_finalize in ONE launch (count = P); `counter` as in hcm_bn_stats_finalize
+int hcm_bn_bwd_reduce_finalize(const float* dz, const float* mask, const float* mask_scale, const float* mask_shift,
+                               const float* y, const float* mean, const float* invstd, long P, int C, float* part,
+                               unsigned int* counter, const float* gamma, float* dgamma, float* dbeta, float* k1, float* k2,
+                               float* k3, cudaStream_t stream) {
+  HCM_CHECK_ARG(dz && y && mean && invstd && part && counter && k1 && k2 && k3 && C >= 1 && C <= 256,
+                "bn_bwd_reduce_finalize: bad args (C=%d)", C);
+  const BwdFin f = {gamma, mean, invstd, dgamma, dbeta, k1, k2, k3};
+  launch_colstat<1>(dz, y, mask, mean, invstd, mask_scale, mask_shift, P, C, part, counter, f, stream);
+  HCM_LAUNCH_CHECK("bn_bwd_reduce_finalize");
   return HCM_OK;
 }
 

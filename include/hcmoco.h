@@ -85,6 +85,17 @@ int hcm_bn_finalize(const float* part, int nparts, int C, long count, const floa
                     float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                     float* scale, float* shift, float* mean, float* invstd, cudaStream_t stream);
 /* out = act(y*scale + shift + (res*res_scale + res_shift)) */
+/* hcm_bn_stats + hcm_bn_finalize (count = P) in ONE launch: the CTA taking the last ticket reduces the partial rows (fp64,
+   fixed order).  `counter`: one zero-initialised uint32 owned by the caller (one per stream); the kernel leaves it at zero. */
+int hcm_bn_stats_finalize(const float* y, long P, int C, float* part, unsigned int* counter, const float* gamma,
+                          const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
+                          float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
+                          cudaStream_t stream);
+/* hcm_bn_bwd_reduce + hcm_bn_bwd_finalize (count = P) in ONE launch; `counter` as above */
+int hcm_bn_bwd_reduce_finalize(const float* dz, const float* mask, const float* mask_scale, const float* mask_shift,
+                               const float* y, const float* mean, const float* invstd, long P, int C, float* part,
+                               unsigned int* counter, const float* gamma, float* dgamma, float* dbeta, float* k1, float* k2,
+                               float* k3, cudaStream_t stream);
 int hcm_bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* res_scale,
                  const float* res_shift, int relu, float* out, long P, int C, cudaStream_t stream);
 /* g = dz * [m > 0] with m = mask (if given) else y*mask_scale+mask_shift (if given) else 1 */

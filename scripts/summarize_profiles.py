@@ -53,14 +53,54 @@ def ncu_rep(path, dst, title):
                     f.write("%-90s %-12s %s\n" % (h, u, v))
 
 
-if os.path.exists(os.path.join(go, "launches_b8.csv")):
-    launches(os.path.join(go, "launches_b8.csv"), os.path.join(out_dir, tag + "_launches_bench_b8.txt"),
-             "bench.py --batch 8 --steps 1 --warmup 3 --no-graph (whole process: build, warm-up, timed step, family profile)")
-for rep in glob.glob(os.path.join(go, "*.ncu-rep")):
-    ncu_rep(rep, os.path.join(out_dir, tag + "_" + os.path.basename(rep).replace(".ncu-rep", ".txt")), os.path.basename(rep))
-for name in ("bench_b64.log", "bench_2gpu.log", "detail_b64.txt"):
-    p = os.path.join(go, name)
-    if os.path.exists(p):
-        with open(p) as f, open(os.path.join(out_dir, tag + "_" + name.replace(".log", ".json")), "w") as g:
-            g.write(f.read())
-print(sorted(os.listdir(out_dir)))
+def rep_rows(path):
+    raw = subprocess.run("ncu -i %s --page raw --csv" % path, shell=True, capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    ci = {h: i for i, h in enumerate(rows[0])}
+    return rows, ci
+
+
+def to_bytes(v, unit):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+
+
+# (report, kernel-name substring) -> key of profiles/ncu_traffic.json (read by bench.py for roofline.traffic)
+TRAFFIC_KEYS = [
+    ("tcconv18_b64", "tc_conv_kernel", "tc_conv 64x64 18->18 k3 s1 B=64"),
+    ("tcwgrad18_b64", "tc_wgrad2_kernel", "tc_wgrad 64x64 18->18 k3 s1 B=64"),
+    ("tcconv144_b64", "tc_conv_kernel", "tc_conv 8x8 144->144 k3 s1 B=64"),
+    ("nce_b64", "nce_logits_kernel", "nce_logits B=64"),
+    ("nce_b64", "nce_bwd_kernel", "nce_bwd B=64"),
+    ("dense_affinity", "dense_affinity_kernel<0>", "dense_affinity_fwd B=32"),
+    ("dense_affinity", "dense_affinity_kernel<1>", "dense_affinity_bwd B=32"),
+]
+
+for name in ("launches_b8.csv", "launches_b64.csv"):
+    if os.path.exists(os.path.join(go, name)):
+        b = name[len("launches_"):-4]
+        launches(os.path.join(go, name), os.path.join(out_dir, tag + "_launches_bench_%s.txt" % b),
+                 "ONE step of bench.py --batch %s --no-graph between cudaProfilerStart/Stop (bench.py --ncu-step)" % b[1:])
+traffic = {}
+tj = os.path.join(out_dir, "ncu_traffic.json")
+if os.path.exists(tj):
+    traffic = json.load(open(tj))
+for rep in sorted(glob.glob(os.path.join(go, "*.ncu-rep"))):
+    base = os.path.basename(rep).replace(".ncu-rep", "")
+    dst = base if base.startswith(tag) else tag + "_" + base
+    ncu_rep(rep, os.path.join(out_dir, dst + ".txt"), base)
+    rows, ci = rep_rows(rep)
+    for frag, kern, key in TRAFFIC_KEYS:
+        if frag not in base:
+            continue
+        for r in rows[2:]:
+            kn = r[ci["Kernel Name"]].replace("(bool)", "")
+            kn = kn.replace("<true>", "<1>").replace("<false>", "<0>")
+            if kern in kn:
+                rd = to_bytes(r[ci["dram__bytes_read.sum"]], rows[1][ci["dram__bytes_read.sum"]])
+                wr = to_bytes(r[ci["dram__bytes_write.sum"]], rows[1][ci["dram__bytes_write.sum"]])
+                traffic[key] = {"dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr,
+                                "us": float(r[ci["gpu__time_duration.sum"]].replace(",", "")),
+                                "source": "profiles/%s.txt (ncu --set full --clock-control none, one launch)" % dst}
+                break
+json.dump(traffic, open(tj, "w"), indent=1, sort_keys=True)

@@ -197,6 +197,15 @@ class TorchKernels:
             nbt += 1
         return 0
 
+    def bn_stats_finalize(self, y, P, C, part, counter, gamma, beta, rm, rv, nbt, momentum, eps, scale, shift, mean, invstd):
+        self.bn_stats(y, P, C, part)
+        return self.bn_finalize(part, self.colstat_rows(P, C), C, P, gamma, beta, rm, rv, nbt, momentum, eps, scale, shift,
+                                mean, invstd)
+
+    def bn_bwd_reduce_finalize(self, dz, mask, msc, msh, y, mean, invstd, P, C, part, counter, gamma, dgamma, dbeta, k1, k2, k3):
+        self.bn_bwd_reduce(dz, mask, msc, msh, y, mean, invstd, P, C, part)
+        return self.bn_bwd_finalize(part, self.colstat_rows(P, C), C, P, gamma, mean, invstd, dgamma, dbeta, k1, k2, k3)
+
     def bn_apply(self, y, scale, shift, res, rs, rh, relu, out, P, C):
         v = _pc(y, P, C)
         if scale is not None:

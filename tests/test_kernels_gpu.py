@@ -150,6 +150,41 @@ def test_batchnorm(KK, PC):
         assert rel(a, b) < 5e-5, (i, rel(a, b))
 
 
+@pytest.mark.parametrize("PC", [(2 * 16 * 16, 18), (64 * 32 * 32, 36), (4096, 64), (39, 128), (8 * 16 * 16, 144), (777, 256),
+                                (64 * 64 * 64, 18)])
+def test_batchnorm_fused_finalize(KK, PC):
+    """bn_stats_finalize / bn_bwd_reduce_finalize (the last CTA reduces the partial rows) == the two-launch forms, bit for bit,
+    and the ticket counter is left re-armed (launched three times in a row)."""
+    P, C = PC
+    kc, _ = KK
+    y = rnd(P, C) * 2 + 0.3
+    gamma, beta = rnd(C, seed=1).abs() + 0.5, rnd(C, seed=2)
+    dz = rnd(P, C, seed=8)
+    rows = kc.colstat_rows(P, C)
+    cnt = torch.zeros(4, dtype=torch.int32, device=DEV)
+
+    def run(fused):
+        part = torch.zeros(rows, 2, C, device=DEV)
+        rm, rv, nbt = torch.zeros(C, device=DEV), torch.ones(C, device=DEV), torch.zeros((), dtype=torch.int64, device=DEV)
+        sc, sh, mu, iv, k1, k2, k3, dg, db = (torch.zeros(C, device=DEV) for _ in range(9))
+        for _ in range(3):
+            if fused:
+                kc.bn_stats_finalize(y, P, C, part, cnt, gamma, beta, rm, rv, nbt, 0.01, 1e-5, sc, sh, mu, iv)
+                kc.bn_bwd_reduce_finalize(dz, None, sc, sh, y, mu, iv, P, C, part, cnt, gamma, dg, db, k1, k2, k3)
+            else:
+                kc.bn_stats(y, P, C, part)
+                kc.bn_finalize(part, rows, C, P, gamma, beta, rm, rv, nbt, 0.01, 1e-5, sc, sh, mu, iv)
+                kc.bn_bwd_reduce(dz, None, sc, sh, y, mu, iv, P, C, part)
+                kc.bn_bwd_finalize(part, rows, C, P, gamma, mu, iv, dg, db, k1, k2, k3)
+        torch.cuda.synchronize()
+        return sc, sh, mu, iv, rm, rv, nbt.float(), k1, k2, k3, dg, db
+
+    a, b = run(True), run(False)
+    assert int(cnt[0]) == 0
+    for i, (u, v) in enumerate(zip(a, b)):
+        assert rel(u, v) < 1e-6, (i, rel(u, v))
+
+
 def test_elementwise_and_layout(KK):
     a, b, g = rnd(1000), rnd(1000, seed=1), rnd(1000, seed=2)
     both(KK, "relu_bwd", [a, b, g, 0, 1000], [2])
