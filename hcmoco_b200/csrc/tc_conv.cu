@@ -30,7 +30,7 @@ constexpr int NTHREADS = NTRANS + 128 + 64;  // then 4 epilogue warps, the TMA p
 constexpr int W_EPI = NTRANS / 32, W_TMA = W_EPI + 4, W_MMA = W_TMA + 1;
 constexpr int MAXG = 16;
 constexpr int MAX_LPAD = 512;
-constexpr int HDR_BYTES = 4096 + 4096;      // barriers / tmem ptr / scale / shift | 4 per-team unit tables; the per-stage source tables follow
+constexpr int HDR_BYTES = 4096 + 6144;      // barriers / tmem ptr / scale / shift | row-concat boundary exchange (2 x 3 warps x 3 rows x 80 floats); the per-stage source tables follow
 constexpr int MAX_ASTAGE = 4;
 constexpr int MAX_UNITS = 256;
 constexpr int MAX_STEPS = 144;                // 9 taps x 256/16 channels
@@ -41,19 +41,44 @@ struct Geo {
   int nqs;           // mode 1: output parities handled per launch (4, 2 or 1 so that N = nqs*Cp <= 256)
   int stride, ks, taps, nq, Hp, Wp, Ho, Wo, center, L, Lpad, Npad, Cin16, SC, SW, KB, cg, ngroups, nblk, nsteps;
   int concat, acc_cols, acc_stages, tmem_cols, nastage, w_resident, wst, spb, grid, V;
+  int rc;            // row-concatenated taps (3x3 stride 1, 3*Npad <= 256): see make_geo
+  int NB;            // N of one weight operand: 3*Npad (rc) or Npad
+  int TM;            // output positions per tile: 126 (rc) or 128
   long Mv, tiles;
   size_t plane_bytes, a_stage_bytes, wslab, wbytes, smem, tab_bytes;
 };
 
+// Row concatenation of the filter-row taps is implemented and parity-green (tests/test_kernels_gpu.py::test_tc_conv_rowcat) but
+// OFF by default.  Measured on B200 (64x64 18->18, B=64, HCM_TC_DEBUG counters): the MMA warp's busy time drops from 53k to 32k
+// cycles per CTA (12 instead of 36 MMAs per tile), but the 4 epilogue warps, which now read 3 accumulator blocks per chunk and
+// exchange boundary rows through a named barrier, become latency-bound at 9.7k cycles per tile (4.4k before): 87 us vs 42 us.
+// Enabling it needs two epilogue warp groups (one per accumulator stage) and TMEM loads issued a chunk ahead.
+// HCM_TC_ROWCAT=1 switches it on for experiments.
+bool rowcat_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("HCM_TC_ROWCAT"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
+bool rowcat_ok(int Cout, int ks, int stride, int mode) {
+  return rowcat_enabled() && mode == 0 && ks == 3 && stride == 1 && 3 * ceil_to(Cout, 16) <= 256;
+}
+
 Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride, int mode = 0) {
   Geo g;
+  // Row concatenation: the three taps (r, 0..2) of a filter row share ONE A operand start (row offset r*Wp) and are the
+  // N blocks of one weight operand: E_s[m'] = sum_r A[m' + r*Wp] * W_(r,s).  The column shift moves to the epilogue,
+  // out[m] = E_0[m] + E_1[m+1] + E_2[m+2] (warp shuffles + a 3-row exchange between the epilogue warps), so a tile yields
+  // 126 outputs from 128 accumulator rows.  An M=128 tcgen05.mma costs ~100 cycles for any N <= 128 and N/2 above
+  // (measured), so narrow layers need 3x fewer MMA slots: 18->18 goes from 36 to 12 MMAs per tile.
+  g.rc = rowcat_ok(Cout, ks, stride, mode) ? 1 : 0;
+  g.TM = g.rc ? TILE_M - 2 : TILE_M;
   g.mode = mode; g.Cp = 0; g.nqs = 0;
   g.stride = stride; g.ks = ks; g.taps = ks * ks;
   g.nq = (stride == 2) ? 4 : 1;
   g.Ho = (stride == 2) ? H / 2 : H;
   g.Wo = (stride == 2) ? W / 2 : W;
   if (ks == 1) { g.Hp = H; g.Wp = W; g.center = 0; g.L = TILE_M; }
-  else if (stride == 1) { g.Hp = H + 2; g.Wp = W + 2; g.center = g.Wp + 1; g.L = TILE_M + 2 * (g.Wp + 1); }
+  else if (stride == 1) { g.Hp = H + 2; g.Wp = W + 2; g.center = g.Wp + 1; g.L = TILE_M + 2 * (g.Wp + 1) - (g.rc ? 2 : 0); }
   else { g.Hp = g.Ho + 1; g.Wp = g.Wo + 1; g.center = g.Wp + 1; g.L = TILE_M + g.Wp + 1; }
   if (mode == 1) {
     // H, W are the OUTPUT (= conv input) size; the staged tensor is dy [B,H/2,W/2,Cin]; virtual grid padded bottom/right
@@ -64,7 +89,7 @@ Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride, int mod
     g.nqs = (4 * g.Cp <= 256) ? 4 : ((2 * g.Cp <= 256) ? 2 : 1);
   }
   g.Mv = (long)B * g.Hp * g.Wp;
-  g.tiles = (g.Mv + TILE_M - 1) / TILE_M;
+  g.tiles = (g.Mv + g.TM - 1) / g.TM;
   g.Lpad = ceil_to(g.L, 16);
   g.Npad = (mode == 1) ? g.nqs * g.Cp : ceil_to(Cout, 16);
   g.Cin16 = ceil_to(Cin, 16);
@@ -80,15 +105,17 @@ Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride, int mod
   g.ngroups = (nblk_all + max_blk - 1) / max_blk;
   g.nblk = (nblk_all + g.ngroups - 1) / g.ngroups;
   g.cg = g.nblk * g.KB;
-  g.nsteps = g.taps * (g.Cin16 / 16);
+  g.NB = g.rc ? 3 * g.Npad : g.Npad;
+  g.nsteps = (g.rc ? 3 : g.taps) * (g.Cin16 / 16);
   g.a_stage_bytes = (size_t)2 * g.nblk * g.plane_bytes;
-  g.concat = (2 * g.Npad <= 256) ? 1 : 0;
-  g.acc_cols = g.concat ? 2 * g.Npad : g.Npad;
+  // (row-concat keeps hi and lo weights as separate operands: the epilogue then reads 3, not 6, accumulator blocks per chunk)
+  g.concat = (!g.rc && 2 * g.NB <= 256) ? 1 : 0;
+  g.acc_cols = g.concat ? 2 * g.NB : g.NB;
   g.acc_stages = (2 * g.acc_cols <= 512) ? 2 : 1;
   int c = 32;
   while (c < g.acc_stages * g.acc_cols) c <<= 1;
   g.tmem_cols = c;
-  g.wslab = (size_t)64 * g.Npad;              // [2 K-chunks][2*Npad rows: hi then lo][16 B]
+  g.wslab = (size_t)64 * g.NB;                // [2 K-chunks][2*NB rows: hi then lo][16 B]
   g.wbytes = (size_t)g.nsteps * g.wslab;
   // A stages: each is filled by its own team of transform warps, so several halo gathers are in flight at once (the
   // gather of a narrow layer is pure latency: ~5 loads per thread); 2..4 stages as shared memory allows
@@ -169,9 +196,10 @@ void build_steps(TcParams& p) {
   for (int grp = 0; grp < g.ngroups; ++grp) {
     const int c_lo = grp * g.cg, c_hi = c_lo + g.cg;
     p.gcount[grp] = 0;
-    for (int tap = 0; tap < g.taps; ++tap) {
+    for (int tap = 0; tap < (g.rc ? 3 : g.taps); ++tap) {
       int q, rowoff;
-      tap_info(g, tap, q, rowoff);
+      if (g.rc) { q = 0; rowoff = tap * g.Wp; }          // one step per filter row: its three taps are N blocks of the operand
+      else tap_info(g, tap, q, rowoff);
       for (int j = 0; j < nj; ++j) {
         const int cs = q * g.Cin16 + 16 * j;
         if (cs < c_lo || cs >= c_hi) continue;
@@ -312,10 +340,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     }
   } else if (warp == W_MMA) {
     // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues tcgen05 =====
-    const uint32_t idesc_n = instr_desc(g.Npad), idesc_2n = instr_desc(2 * g.Npad);
+    const uint32_t idesc_n = instr_desc(g.NB), idesc_2n = instr_desc(2 * g.NB);
     const uint32_t a0 = smem_u32(Abase), w0 = smem_u32(Wbase);
     const uint64_t a_t = sw_desc_template(SW);
-    const uint32_t b_lbo = (uint32_t)(2 * g.Npad) * 16;
+    const uint32_t b_lbo = (uint32_t)(2 * g.NB) * 16;
     const uint64_t b_t = smem_desc(0, b_lbo, 128);                         // no-swizzle K-major weight slab
     long long c_acc = 0, c_a = 0, c_all = clock64(), tq;
     if (g.w_resident) mbar_wait(BAR(12), 0);
@@ -351,7 +379,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
                 umma_bf16(d, al, bw, idesc_n, 1u);                          // += A_lo*w_hi (first Np rows of the slab)
               } else {
                 umma_bf16(d, ah, bw, idesc_n, first);
-                umma_bf16(d, ah, bw + (uint64_t)(g.Npad), idesc_n, 1u);     // lo rows start Npad*16 bytes further
+                umma_bf16(d, ah, bw + (uint64_t)(g.NB), idesc_n, 1u);     // lo rows start Npad*16 bytes further
                 umma_bf16(d, al, bw, idesc_n, 1u);
               }
               first = 1u;
@@ -377,7 +405,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
                 umma_bf16(d, al, bw, idesc_n, 1u);
               } else {
                 umma_bf16(d, ah, bw, idesc_n, first);
-                umma_bf16(d, ah, bw + (uint64_t)(g.Npad), idesc_n, 1u);
+                umma_bf16(d, ah, bw + (uint64_t)(g.NB), idesc_n, 1u);
                 umma_bf16(d, al, bw, idesc_n, 1u);
               }
               if (last) umma_commit(BAR(32 + rs));
@@ -404,7 +432,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     for (long f = team; f < nfills; f += g.nastage) {
       {
         const int ti = (int)(f / g.ngroups), grp = (int)(f - (long)ti * g.ngroups);
-        const long tile0 = ((long)blockIdx.x + (long)ti * gridDim.x) * TILE_M;
+        const long tile0 = ((long)blockIdx.x + (long)ti * gridDim.x) * g.TM;
         const int s = team;
         tq = clock64();
         mbar_wait(BAR(4 + s), (uint32_t)(((f / g.nastage) & 1) ^ 1));
@@ -438,14 +466,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     long long c_wait = 0, c_all = clock64(), tq;
     const bool vec4 = (p.Cout % 4) == 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
-      const long tile0 = ((long)blockIdx.x + (long)ti * gridDim.x) * TILE_M;
+      const long tile0 = ((long)blockIdx.x + (long)ti * gridDim.x) * g.TM;
       const int as = ti % g.acc_stages;
-      const int px = virt_to_dst(tile0 + m, p);
+      const int px = (m < g.TM) ? virt_to_dst(tile0 + m, p) : -1;   // row-concat tiles: rows 126, 127 belong to the next tile
       float* yp = p.y + (long)(px < 0 ? 0 : px) * p.Cout;   // indexed [c0 + i] below
       tq = clock64();
       mbar_wait(BAR(8 + as), (uint32_t)((ti / g.acc_stages) & 1));
       c_wait += clock64() - tq;
       tc_fence_after();
+      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * g.acc_cols);
+      // row-concat boundary exchange: [tile parity][chunk][warp 1..3][E_1 row 0, E_2 row 0, E_2 row 1][16]
+      float* xch = reinterpret_cast<float*>(smem + 4096) + (ti & 1) * (5 * 3 * 3 * 16);
       for (int c0 = 0; c0 < g.Npad; c0 += 16) {
         if (g.mode == 1) {
           // parity block qq = c0 / Cp of the 2x2 output pixels of this position; channel offset inside the block
@@ -453,13 +484,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
           yp = p.y + ((long)(px < 0 ? 0 : px) + (long)(qq >> 1) * p.W + (qq & 1)) * p.Cout - c0 + cc;
         }
         float v[16];
-        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * g.acc_cols + c0);
-        tmem_ld16(tbase, v);
-        if (g.concat) {
-          float u[16];
-          tmem_ld16(tbase + (uint32_t)g.Npad, u);
+        if (g.rc) {
+          // out[m] = E_0[m] + E_1[m+1] + E_2[m+2]: the column taps are row shifts of the accumulator.  Within a warp the
+          // shift is a shuffle; rows 0 and 1 of warps 1..3 publish E_1[row 0], E_2[row 0], E_2[row 1] for lanes 30 / 31 of
+          // the previous warp (one 128-thread named barrier per chunk).
+          float e1[16], e2[16];
+          tmem_ld16_issue(trow + (uint32_t)c0, v);
+          tmem_ld16_issue(trow + (uint32_t)(g.Npad + c0), e1);
+          tmem_ld16_issue(trow + (uint32_t)(2 * g.Npad + c0), e2);
+          tmem_ld_wait();
+          float* xc = xch + (c0 >> 4) * (3 * 3 * 16);
+          if (q > 0 && lane < 2) {
+            float* o = xc + (q - 1) * 3 * 16;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += u[i];
+            for (int i = 0; i < 16; ++i) {
+              if (lane == 0) o[i] = e1[i];
+              o[(1 + lane) * 16 + i] = e2[i];
+            }
+          }
+          asm volatile("bar.sync 6, 128;" ::: "memory");
+          const float* nx = xc + q * 3 * 16;                  // published by warp q+1
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float t1 = __shfl_down_sync(0xffffffffu, e1[i], 1), t2 = __shfl_down_sync(0xffffffffu, e2[i], 2);
+            if (q < 3) {
+              if (lane == 31) t1 = nx[i];
+              if (lane >= 30) t2 = nx[(1 + lane - 30) * 16 + i];
+            }
+            v[i] += t1 + t2;
+          }
+        } else {
+          const uint32_t tbase = trow + (uint32_t)c0;
+          tmem_ld16(tbase, v);
+          if (g.concat) {
+            float u[16];
+            tmem_ld16(tbase + (uint32_t)g.Npad, u);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += u[i];
+          }
         }
         const int cend = (g.mode == 1) ? (c0 / g.Cp) * g.Cp + p.Cout : p.Cout;      // first invalid column
         if (px >= 0) {
@@ -508,9 +570,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
 __global__ void tc_pack_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, Geo g, int Cin, int Cout, int transpose,
                                int wCin) {
   const int nj = g.Cin16 / 16;
-  const int step = blockIdx.x;
+  const int step = blockIdx.x;                   // one block per (tap, K step), whatever the layout
   const int tap = step / nj, j = step - tap * nj;
-  uint8_t* slab = out + (size_t)step * g.wslab;
+  uint8_t* slab = out + (size_t)step * 64 * g.Npad;
   for (int e = threadIdx.x; e < g.Npad * 16; e += blockDim.x) {
     const int n = e >> 4, k = e & 15;
     const int c = 16 * j + k;
@@ -519,6 +581,15 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, uint8_t* __restrict_
       v = transpose ? w[((long)c * wCin + n) * g.taps + (g.taps - 1 - tap)] : w[((long)n * wCin + c) * g.taps + tap];
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    if (g.rc) {
+      // row-concat layout: one slab per (filter row r, K step j); rows [s*Npad + n] = hi of tap (r,s), then the lo rows
+      const int r = tap / 3, s = tap - 3 * r;
+      uint8_t* rslab = out + (size_t)(r * nj + j) * g.wslab;
+      const size_t chunk = (size_t)(k >> 3) * (2 * g.NB) * 16;
+      *reinterpret_cast<__nv_bfloat16*>(rslab + chunk + (size_t)(s * g.Npad + n) * 16 + (k & 7) * 2) = hi;
+      *reinterpret_cast<__nv_bfloat16*>(rslab + chunk + (size_t)(g.NB + s * g.Npad + n) * 16 + (k & 7) * 2) = lo;
+      continue;
+    }
     const size_t chunk = (size_t)(k >> 3) * (2 * g.Npad) * 16;
     *reinterpret_cast<__nv_bfloat16*>(slab + chunk + (size_t)n * 16 + (k & 7) * 2) = hi;
     *reinterpret_cast<__nv_bfloat16*>(slab + chunk + (size_t)(g.Npad + n) * 16 + (k & 7) * 2) = lo;
@@ -566,7 +637,8 @@ __global__ void tc_pack_batch_kernel(const PackJob* __restrict__ jobs, int njobs
   }
   __syncthreads();
   const float* w = reinterpret_cast<const float*>(jb.w);
-  const int Cin = (int)jb.Cin, Cout = (int)jb.Cout, ks = (int)jb.ks, mode = (int)jb.mode;
+  const int Cin = (int)jb.Cin, Cout = (int)jb.Cout, ks = (int)jb.ks, mode = (int)jb.mode & 3;
+  const bool rc = ((int)jb.mode & 4) != 0;                        // row-concat layout (see tc_pack_kernel)
   const int step = (int)((long long)blockIdx.x - jb.first);
   int Npad, Cin16, taps, Cp = 0;
   int q0 = 0;
@@ -595,6 +667,14 @@ __global__ void tc_pack_batch_kernel(const PackJob* __restrict__ jobs, int njobs
     }
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    if (rc) {
+      const int r = tap / 3, s = tap - 3 * r, NB = 3 * Npad;
+      uint8_t* rslab = reinterpret_cast<uint8_t*>(jb.out) + (size_t)(r * nj + j) * 64 * NB;
+      const size_t chunk = (size_t)(k >> 3) * (2 * NB) * 16;
+      *reinterpret_cast<__nv_bfloat16*>(rslab + chunk + (size_t)(s * Npad + n) * 16 + (k & 7) * 2) = hi;
+      *reinterpret_cast<__nv_bfloat16*>(rslab + chunk + (size_t)(NB + s * Npad + n) * 16 + (k & 7) * 2) = lo;
+      continue;
+    }
     const size_t chunk = (size_t)(k >> 3) * (2 * Npad) * 16;
     *reinterpret_cast<__nv_bfloat16*>(slab + chunk + (size_t)n * 16 + (k & 7) * 2) = hi;
     *reinterpret_cast<__nv_bfloat16*>(slab + chunk + (size_t)(Npad + n) * 16 + (k & 7) * 2) = lo;
@@ -687,7 +767,7 @@ int hcm_tc_dgrad_s2(const float* dy, const void* wpack, float* dx, int B, int H,
 }
 
 // One launch for all weight packs of a step.  jobs (device): njobs x 8 int64 {w ptr, out ptr, Cin, Cout, ks, mode, ldw, first_step}
-// with mode 0 = hcm_tc_conv_pack(transpose 0), 1 = (transpose 1), 2 = hcm_tc_dgrad_s2_pack; (Cin, Cout) as passed to those calls;
+// with mode 0 = hcm_tc_conv_pack(flags 0), 1 = (flags 1), +4 = row-concatenated layout, 2 = hcm_tc_dgrad_s2_pack; (Cin, Cout) as passed to those calls;
 // first_step = running sum of the jobs' K-step counts (ks*ks*ceil16(Cin)/16, mode 2: 4*ceil16(Cout)/16); total_steps = their sum.
 int hcm_tc_pack_batch(const long long* jobs, int njobs, int total_steps, cudaStream_t stream) {
   HCM_CHECK_ARG(jobs && njobs >= 1 && total_steps >= 1, "tc_pack_batch: bad args");
@@ -709,17 +789,25 @@ long hcm_tc_conv_wpack_bytes(int B, int H, int W, int Cin, int Cout, int ks) {
   return (long)g.wbytes;
 }
 
+// 1 if hcm_tc_conv runs this convolution with row-concatenated taps (3x3, stride 1, 3*ceil16(Cout) <= 256): its weights
+// must then be packed with flag 4 (the layout differs).  For the data gradient pass the GEMM's Cout (= Cin of the weight).
+int hcm_tc_conv_rowcat_supported(int Cout, int ks, int stride) { return rowcat_ok(Cout, ks, stride, 0) ? 1 : 0; }
+
 // Pack OIHW fp32 weights into the bf16 hi/lo K-step slabs.  `w` may point at a column block of a wider
-// [O][ldw][ks][ks] tensor (ldw = 0: contiguous).  (Cin, Cout) describe the GEMM being run: transpose=0 -> the forward conv
-// of w[Cout][Cin][ks][ks] (any stride);  transpose=1 -> the data gradient of a STRIDE-1 conv, i.e. a conv with
-// Cin' = Cout(w), Cout' = Cin(w): pass Cin = Cout(w), Cout = Cin(w).
-int hcm_tc_conv_pack(const float* w, int ldw, void* wpack, int B, int H, int W, int Cin, int Cout, int ks, int transpose,
+// [O][ldw][ks][ks] tensor (ldw = 0: contiguous).  (Cin, Cout) describe the GEMM being run.  flags:
+//   bit 0 (1): transpose -> the data gradient of a STRIDE-1 conv, i.e. a conv with Cin' = Cout(w), Cout' = Cin(w): pass
+//              Cin = Cout(w), Cout = Cin(w);  clear -> the forward conv of w[Cout][Cin][ks][ks] (any stride)
+//   bit 2 (4): row-concatenated layout, required iff hcm_tc_conv_rowcat_supported(Cout, ks, stride of the consumer)
+int hcm_tc_conv_pack(const float* w, int ldw, void* wpack, int B, int H, int W, int Cin, int Cout, int ks, int flags,
                      cudaStream_t stream) {
   HCM_CHECK_ARG(w && wpack, "tc_conv_pack: null pointer");
   HCM_CHECK_ARG(Cin <= 256 && Cout <= 256 && (ks == 1 || ks == 3), "tc_conv_pack: unsupported geometry");
+  const int transpose = flags & 1;
   Geo g = make_geo(B, H, W, Cin, Cout, ks, 1);
+  HCM_CHECK_ARG(!(flags & 4) || g.rc, "tc_conv_pack: row-concatenated layout requested for an ineligible convolution");
+  if (!(flags & 4)) { g.rc = 0; g.NB = g.Npad; g.wslab = (size_t)64 * g.Npad; }
   const int wCin = ldw > 0 ? ldw : (transpose ? Cout : Cin);
-  tc_pack_kernel<<<g.nsteps, 256, 0, stream>>>(w, reinterpret_cast<uint8_t*>(wpack), g, Cin, Cout, transpose, wCin);
+  tc_pack_kernel<<<g.taps * (g.Cin16 / 16), 256, 0, stream>>>(w, reinterpret_cast<uint8_t*>(wpack), g, Cin, Cout, transpose, wCin);
   HCM_LAUNCH_CHECK("tc_conv_pack");
   return HCM_OK;
 }

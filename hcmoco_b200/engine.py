@@ -405,7 +405,7 @@ class Engine:
             nb = K.tc_conv_wpack_bytes(B, H, W, cin, cout, ks)
             wp_f = K.empty((nb + 3) // 4)
             rows = K.colstat_rows(P, cout)
-            self._pack_job(w, 0, wp_f, (B, H, W), cin, cout, ks, 0)
+            self._pack_job(w, 0, wp_f, (B, H, W), cin, cout, ks, 4 * K.tc_conv_rowcat_supported(cout, ks, stride))
             assert rows * 2 * cout <= self.part.numel()
             p.f(K.tc_conv, x.data, wp_f, None, y, B, H, W, cin, cout, ks, stride, x.scale, x.shift, int(x.relu), 0)
             self._bn_stats(y, P, cout, bk, BN2D_MOMENTUM, scale, shift, mean, invstd)
@@ -446,7 +446,7 @@ class Engine:
                     # data gradient = the same tensor-core conv run on dy with transposed + flipped weights
                     nbt = K.tc_conv_wpack_bytes(B, H, W, cout, cin, ks)
                     wp_t = K.empty((nbt + 3) // 4)
-                    self._pack_job(w, 0, wp_t, (B, H, W), cout, cin, ks, 1)
+                    self._pack_job(w, 0, wp_t, (B, H, W), cout, cin, ks, 1 + 4 * K.tc_conv_rowcat_supported(cin, ks, 1))
                     p.b(K.tc_conv, dy, wp_t, None, gx, B, H, W, cout, cin, ks, 1, None, None, 0, acc)
                 elif tc and stride == 2 and ks == 3 and K.tc_dgrad_s2_supported(B, H, W, cin, cout):
                     nbt2 = K.tc_dgrad_s2_wpack_bytes(B, H, W, cin, cout)

@@ -50,10 +50,15 @@ int hcm_gemm(const float* A, const float* Bm, const float* bias, float* C, int b
  *      68-75, 187-216 and the 1x1 projection build_backbone.py:243-245; forward and data gradient ---- */
 int hcm_tc_conv_supported(int B, int H, int W, int Cin, int Cout, int ks, int stride);
 long hcm_tc_conv_wpack_bytes(int B, int H, int W, int Cin, int Cout, int ks);
-/* transpose=0: pack w[Cout][Cin][ks][ks] for the forward conv; transpose=1: pack the same tensor for its data
- * gradient seen as a conv with Cin' = Cout(w), Cout' = Cin(w) (pass those as Cin, Cout).  ldw > 0: `w` is a column block
+/* 1 if hcm_tc_conv runs the convolution with row-concatenated taps (3x3, stride 1, 3*ceil16(Cout) <= 256: the three taps of a
+ * filter row are the N blocks of ONE tcgen05.mma, the column shift is resolved in the epilogue); its weights must then be packed
+ * with flag 4.  For the data gradient pass the GEMM's Cout (= Cin of the weight) */
+int hcm_tc_conv_rowcat_supported(int Cout, int ks, int stride);
+/* flags bit 0 clear: pack w[Cout][Cin][ks][ks] for the forward conv; set: pack the same tensor for its data gradient seen as
+ * a conv with Cin' = Cout(w), Cout' = Cin(w) (pass those as Cin, Cout).  flags bit 2 (4): row-concatenated layout, required iff
+ * hcm_tc_conv_rowcat_supported(Cout, ks, stride of the consuming conv).  ldw > 0: `w` is a column block
  * of a wider [O][ldw][ks][ks] tensor (per-branch blocks of the 1x1 projection); lddw likewise for hcm_tc_wgrad */
-int hcm_tc_conv_pack(const float* w, int ldw, void* wpack, int B, int H, int W, int Cin, int Cout, int ks, int transpose,
+int hcm_tc_conv_pack(const float* w, int ldw, void* wpack, int B, int H, int W, int Cin, int Cout, int ks, int flags,
                      cudaStream_t stream);
 /* all weight packs of a step in one launch: jobs (device) = njobs x 8 int64 {w ptr, out ptr, Cin, Cout, ks, mode, ldw, first_step};
  * mode 0/1 = hcm_tc_conv_pack(transpose 0/1), 2 = hcm_tc_dgrad_s2_pack, (Cin, Cout) as passed to those calls */

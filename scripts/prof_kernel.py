@@ -17,7 +17,7 @@ y = torch.empty(B, H, W, Cout, device="cuda")
 dw = torch.zeros_like(w)
 sc, sh = torch.rand(Cin, device="cuda") + 0.5, torch.randn(Cin, device="cuda")
 wp = torch.zeros((K.tc_conv_wpack_bytes(B, H, W, Cin, Cout, ks) + 3) // 4, device="cuda")
-K.tc_conv_pack(w, 0, wp, B, H, W, Cin, Cout, ks, 0)
+K.tc_conv_pack(w, 0, wp, B, H, W, Cin, Cout, ks, 4 * K.tc_conv_rowcat_supported(Cout, ks, 1))
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 for i in range(reps):
     K.tc_conv(x, wp, None, y, B, H, W, Cin, Cout, ks, 1, sc, sh, 1, 0)

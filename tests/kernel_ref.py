@@ -108,7 +108,11 @@ class TorchKernels:
     def tc_conv_wpack_bytes(self, B, H, W, Cin, Cout, ks):
         return Cin * Cout * ks * ks * 8          # room for fp64 in the exact-wiring tests
 
-    def tc_conv_pack(self, w, ldw, wpack, B, H, W, Cin, Cout, ks, transpose):
+    def tc_conv_rowcat_supported(self, Cout, ks, stride):
+        return 0          # a layout detail of the CUDA kernel; the reference "pack" is the plain fp32 weight
+
+    def tc_conv_pack(self, w, ldw, wpack, B, H, W, Cin, Cout, ks, flags):
+        transpose = flags & 1
         # the "packed" form of the reference is simply the effective OIHW weight of the GEMM being run
         O, I = (Cin, Cout) if transpose else (Cout, Cin)                         # dims of the OIHW slice
         ld = ldw if ldw > 0 else I

@@ -407,7 +407,7 @@ def test_tc_conv(KK, shape):
     sc, sh = rnd(Cin, seed=1).abs() + 0.5, rnd(Cin, seed=2)
     bias = rnd(Cout, seed=5)
     wp = torch.zeros((kc.tc_conv_wpack_bytes(B, H, W, Cin, Cout, ks) + 3) // 4, device=DEV)
-    kc.tc_conv_pack(w, 0, wp, B, H, W, Cin, Cout, ks, 0)
+    kc.tc_conv_pack(w, 0, wp, B, H, W, Cin, Cout, ks, 4 * kc.tc_conv_rowcat_supported(Cout, ks, 1))
     y1, y2 = rnd(B, H, W, Cout, seed=7), rnd(B, H, W, Cout, seed=7)
     # forward, BN+ReLU applied on load
     kc.tc_conv(x, wp, None, y1, B, H, W, Cin, Cout, ks, 1, sc, sh, 1, 0)
@@ -422,11 +422,24 @@ def test_tc_conv(KK, shape):
     if kc.tc_conv_supported(B, H, W, Cout, Cin, ks, 1):
         dy = rnd(B, H, W, Cout, seed=9)
         wpt = torch.zeros((kc.tc_conv_wpack_bytes(B, H, W, Cout, Cin, ks) + 3) // 4, device=DEV)
-        kc.tc_conv_pack(w, 0, wpt, B, H, W, Cout, Cin, ks, 1)
+        kc.tc_conv_pack(w, 0, wpt, B, H, W, Cout, Cin, ks, 1 + 4 * kc.tc_conv_rowcat_supported(Cin, ks, 1))
         dx1, dx2 = torch.zeros(B, H, W, Cin, device=DEV), torch.zeros(B, H, W, Cin, device=DEV)
         kc.tc_conv(dy, wpt, None, dx1, B, H, W, Cout, Cin, ks, 1, None, None, 0, 0)
         kr.conv2d_dgrad(dy, w, dx2, B, H, W, Cin, Cout, ks, 1, 0)
         assert rel(dx1, dx2) < 3e-5, rel(dx1, dx2)
+
+
+def test_tc_conv_rowcat():
+    """The experimental row-concatenated formulation of tc_conv (HCM_TC_ROWCAT=1; off by default, see tc_conv.cu) stays
+    parity-green: the same tc_conv cases in a child process with the switch on (the library reads it once per process)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, HCM_TC_ROWCAT="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_kernels_gpu.py"), "-q", "-x", "-m", "gpu", "-k",
+                        "test_tc_conv and not rowcat and not stride2"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
 
 
 @pytest.mark.parametrize("shape", TC_CONVS)
