@@ -92,6 +92,7 @@ struct WParams {
   const float* dy;
   float* dw;
   int B, H, W, Cin, Cout, lddw;
+  long long* dbg;              // HCM_TC_DEBUG=1: per-CTA cycle counters of the three roles
   WGeo g;
 };
 
@@ -206,9 +207,12 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
       }
     }
     __syncwarp();
+    long long c_all = clock64(), c_wait = 0, tq;
     for (int it = 0; it < ntiles; ++it) {
       const int s = it % g.nstage;
+      tq = clock64();
       mbar_wait(BAR(s), (uint32_t)((it / g.nstage) & 1));
+      c_wait += clock64() - tq;
       tc_fence_after();
       const uint32_t st = s0 + (uint32_t)s * (uint32_t)g.stage_bytes;
       for (int k = 0; k < TILE / 16; ++k) {
@@ -231,13 +235,18 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
       if (elect_one()) umma_commit(BAR(4 + s));
     }
     if (elect_one()) umma_commit(BAR(8));
+    if (p.dbg && lane == 0) { long long* o = p.dbg + (long)blockIdx.x * 8; o[0] = clock64() - c_all; o[1] = c_wait; }
   } else if (warp < W_EPI) {
     // ===== transform teams: team k stages tiles k, k+nstage, ... into stage k =====
     const int TS = NTRANS / g.nstage;
     const int team = threadIdx.x / TS, t = threadIdx.x - team * TS;
+    long long c_all = clock64(), c_wait = 0, c_tab = 0, tq;
     for (int it = team; it < ntiles; it += g.nstage) {
       const int s = team;
+      tq = clock64();
       mbar_wait(BAR(4 + s), (uint32_t)(((it / g.nstage) & 1) ^ 1));
+      c_wait += clock64() - tq;
+      tq = clock64();
       const long tile0 = (t_beg + it) * TILE;
       int* tab = s_tab + s * tab_stride;
       int* dtab = tab + g.Lpad * g.nq;
@@ -250,6 +259,7 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
         if (m >= 0 && m < TILE) dtab[m] = d;
       }
       asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TS) : "memory");
+      c_tab += clock64() - tq;
       uint8_t* st = Sbase + (size_t)s * g.stage_bytes;
       // dy tile: channels [co_lo, co_lo + co_n)
       if (g.Vd == 4) stage_rows8<4>(p.dy, p.Cout, co_lo, co_n, TILE, dtab, 1, 0, st, d_lo, (uint32_t)g.d_plane, SWd, 0, nullptr, nullptr, false, 0, t, TS);
@@ -264,19 +274,66 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
       fence_proxy_async();
       mbar_arrive(BAR(s));
     }
-  } else {
-    // ===== epilogue warps: D[co][tap*CI + ci] -> dw (fp32 atomics) =====
+    if (p.dbg && threadIdx.x == 0) { long long* o = p.dbg + (long)blockIdx.x * 8; o[2] = clock64() - c_all; o[3] = c_wait; o[4] = c_tab; }
+  }
+  // ===== drain: D[co][tap*CI + ci] -> dw.  EVERY warp helps (a warp may read the TMEM lane quarter warp%4): the 4 dedicated
+  // warps alone need ~6k dependent instructions each for this, 13-26 us of a 45-75 us kernel (measured); 20 warps share it.
+  // The CTA's block of dw is assembled in shared memory in the GLOBAL layout [co][ci][tap] (the staging tiles are free once
+  // every MMA has completed), then added to global memory with coalesced atomics.
+  {
+    const long long c_all = clock64();
     mbar_wait(BAR(8), 0);
+    const long long c_w = clock64() - c_all;
+    if (p.dbg && warp == W_EPI && lane == 0) { long long* o = p.dbg + (long)blockIdx.x * 8; o[6] = c_w; o[7] = clock64(); }
     tc_fence_after();
-    const int q = warp & 3;
+    const int q = warp & 3, wsub = warp >> 2;                     // lane quarter; helper index among the warps of that quarter
+    constexpr int NSUB = (NTHREADS_W / 32) / 4;                   // 5 full helper sets (warps 0..19); the MMA warp sits out
+    const bool helper = wsub < NSUB;
     const int m = q * 32 + lane, bw = (int)SWd / 2;
     // accumulator row -> output channel: rows [0, co_n) are dy_hi products; with a single dy plane rows [bw, bw + co_n) are
     // the dy_lo products of the same channels (see `fold` in the MMA warp)
     const int cr = (m < co_n) ? m : ((g.d_blocks == 1 && m >= bw && m - bw < co_n) ? m - bw : -1);
-    const int co = co_lo + cr;
     const bool rowok = cr >= 0 && ntiles > 0;
-    for (int tap = 0; tap < g.taps; ++tap) {
-      for (int c0 = 0; c0 < g.CI; c0 += 16) {
+    const int RL = ci_n * g.taps, RLp = RL | 1;                  // row length / odd row pitch (floats)
+    float* red = reinterpret_cast<float*>(Sbase);
+    const int nch = (ci_n + 15) / 16;                            // 16-column chunks per tap
+    if ((size_t)co_n * RLp * 4 <= (size_t)g.nstage * g.stage_bytes) {
+      // pass 0: the dy_hi rows store their values; pass 1 (single dy plane only): the dy_lo rows add theirs.  Every slot has
+      // exactly one writer per pass, so plain shared-memory stores suffice (a shared fp32 atomicAdd is a CAS loop)
+      const int npass = (g.d_blocks == 1) ? 2 : 1;
+      for (int pass = 0; pass < npass; ++pass) {
+        const bool mine = rowok && ((pass == 0) == (m < co_n));
+        if (helper) {
+          for (int j = wsub; j < g.taps * nch; j += NSUB) {
+            const int tap = j / nch, c0 = (j - tap * nch) * 16;
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * g.CI + c0), v);
+            if (mine) {
+              float* o = red + cr * RLp + c0 * g.taps + tap;
+              if (c0 + 16 <= ci_n) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i * g.taps] = (pass == 0) ? v[i] : o[i * g.taps] + v[i];
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (c0 + i < ci_n) o[i * g.taps] = (pass == 0) ? v[i] : o[i * g.taps] + v[i];
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (ntiles > 0) {
+        for (int e = threadIdx.x; e < co_n * RL; e += NTHREADS_W) {
+          const int row = e / RL, col = e - row * RL;
+          atomicAdd(p.dw + ((long)(co_lo + row) * p.lddw + ci_lo) * g.taps + col, red[row * RLp + col]);
+        }
+      }
+    } else if (helper) {
+      // (block too large for the staging area: direct scatter)
+      const int co = co_lo + cr;
+      for (int j = wsub; j < g.taps * nch; j += NSUB) {
+        const int tap = j / nch, c0 = (j - tap * nch) * 16;
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * g.CI + c0), v);
         if (rowok) {
@@ -289,6 +346,7 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
       }
     }
   }
+  if (p.dbg && warp == W_EPI && lane == 0) { long long* o = p.dbg + (long)blockIdx.x * 8; o[5] = clock64(); }
   tc_fence_before();
   __syncthreads();
   if (warp == W_MMA) tmem_dealloc(tmem, g.tmem_cols);
@@ -322,9 +380,23 @@ int hcm_tc_wgrad(const float* x, const float* dy, float* dw, int lddw, int B, in
     if (e != cudaSuccess) { hcm_set_error("tc_wgrad: smem attribute: %s", cudaGetErrorString(e)); return HCM_ERR_CUDA; }
     configured = true;
   }
+  static long long* dbg = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    dbg_on = getenv("HCM_TC_DEBUG") ? 1 : 0;
+    if (dbg_on) cudaMalloc(&dbg, 1024 * 8 * sizeof(long long));
+  }
+  p.dbg = dbg;
   dim3 grid(p.g.ntr, p.g.nsplit, p.g.nblk);
   tc_wgrad2_kernel<<<grid, NTHREADS_W, p.g.smem, stream>>>(p);
   HCM_LAUNCH_CHECK("tc_wgrad");
+  if (dbg_on) {
+    long long h[8];
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc_wgrad dbg] %dx%d %d->%d k%d s%d tiles/cta %d stages %d | mma: total %lld wait %lld | transform(team 0): total %lld "
+            "wait %lld table %lld | epilogue: wait %lld drain %lld\n", H, W, Cin, Cout, ks, stride, p.g.tiles_per, p.g.nstage, h[0], h[1],
+            h[2], h[3], h[4], h[6], h[5] - h[7]);
+  }
   return HCM_OK;
 }
 
