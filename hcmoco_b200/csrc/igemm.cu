@@ -334,8 +334,11 @@ int pick_pm(long M) {
 }
 
 template <int MODE>
-int launch(const IgemmParams& p, long M, int N, int gz, cudaStream_t st, const char* name, int* grid_m_out) {
-  const int pm = pick_pm(M), cn = pick_cn(N);
+int launch(const IgemmParams& p, long M, int N, int gz, cudaStream_t st, const char* name, int* grid_m_out, bool small_tiles = false) {
+  int pm = pick_pm(M), cn = pick_cn(N);
+  // plain GEMMs only (the conv modes report their partial-row count from pick_pm): when the 128 x 64 tiling leaves most
+  // SMs idle (SemGCN: 1024 x 128 outputs = 16 CTAs, 126 us per launch measured) use 64 x 32 tiles
+  if (small_tiles && (long)hcm_cdiv(M, 16 * pm) * hcm_cdiv(N, 8 * cn) * gz < 148) { pm = 4; if (N > 24) cn = 4; }
   dim3 grid(hcm_cdiv(M, 16 * pm), hcm_cdiv(N, 8 * cn), gz);
   if (grid_m_out) *grid_m_out = grid.x;
 #define HCM_CASE(PM_, CN_) \
@@ -423,7 +426,7 @@ int hcm_gemm(const float* A, const float* Bm, const float* bias, float* C, int b
   p.A = A; p.Bm = Bm; p.C = C; p.bias = bias; p.M = M; p.N = N; p.K = K;
   p.sAm = sAm; p.sAk = sAk; p.sBk = sBk; p.sBn = sBn; p.sCm = sCm; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC;
   p.alpha = alpha; p.accumulate = accumulate;
-  return launch<MODE_GEMM>(p, M, N, batch, stream, "gemm", nullptr);
+  return launch<MODE_GEMM>(p, M, N, batch, stream, "gemm", nullptr, true);
 }
 
 }  // extern "C"
