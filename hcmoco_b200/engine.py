@@ -129,28 +129,34 @@ class Plan:
     invoked in reverse op order by `finish()`, so that first-writer / accumulate flags of gradient
     buffers are resolved statically.
 
-    Every launch carries a stream tag (0 = main, 1 = side): the two HRNet encoders are independent between the input
-    split and the heads, so encoder2's launches go to a side stream (forked / joined with events, captured into the
-    same CUDA graph); its small-grid and elementwise kernels then fill the SMs the other encoder's kernels leave idle."""
+    Every launch carries a stream tag.  Tag 0 is the stream the program is run on; `fork(parent, children)` lets the
+    children's streams start from the parent's current position, `join(parent, children)` makes the parent wait for them
+    (events; everything is captured into the same CUDA graph).  Both register the mirrored marker for the backward program.
+    Used at two levels: encoder2 (+ the skeleton encoder) beside encoder1, and inside every HR module the branches 1..3
+    beside branch 0 — the low-resolution branches have 50-160 tiles for 148 SMs and are latency-bound, so their kernels
+    fill the SMs (and the gaps between the kernels) of the high-resolution branch instead of running alone."""
 
     def __init__(self, K):
         self.K = K
         self.fwd, self.bwd, self._builders = [], [], []
         self.tag = 0
-        self.side = None
-        self._bwd_forked = False
+        self.streams = {}
 
     def f(self, fn, *args):
         self.fwd.append((fn, args, self.tag))
 
     def b(self, fn, *args):
-        if self.tag == 1 and not self._bwd_forked:
-            self.bwd.append((FORK, (), 0))
-            self._bwd_forked = True
         self.bwd.append((fn, args, self.tag))
 
-    def mark_f(self, what):
-        self.fwd.append((what, (), 0))
+    def fork(self, parent, children):
+        children = tuple(children)
+        self.fwd.append((FORK, (parent, children), parent))
+        self._builders.append((lambda: self.bwd.append((JOIN, (parent, children), parent)), parent))
+
+    def join(self, parent, children):
+        children = tuple(children)
+        self.fwd.append((JOIN, (parent, children), parent))
+        self._builders.append((lambda: self.bwd.append((FORK, (parent, children), parent)), parent))
 
     def on_backward(self, builder):
         self._builders.append((builder, self.tag))
@@ -165,8 +171,6 @@ class Plan:
             self.tag = tag
             bld()
         self.tag = 0
-        if self._bwd_forked:
-            self.bwd.append((JOIN, (), 0))
         self._builders = []
         return n
 
@@ -188,43 +192,47 @@ class Plan:
         return act.grad
 
     def run(self, prog, two_streams=True):
-        """Enqueue a program.  With a CUDA device and two_streams, tag-1 launches between FORK and JOIN go to the side stream."""
-        use_side = two_streams and self.K.device == "cuda" and any(e[0] == FORK for e in prog)
+        """Enqueue a program.  With a CUDA device and two_streams, launches go to the stream of their tag (tag 0 = the
+        current stream); otherwise everything runs in program order on the current stream."""
+        use_side = two_streams and self.K.device == "cuda" and any(e[0] is FORK for e in prog)
         if not use_side:
             for fn, args, _ in prog:
                 if fn is not FORK and fn is not JOIN:
                     fn(*args)
             return
-        if self.side is None:
-            self.side = torch.cuda.Stream()
-        main, side, forked = torch.cuda.current_stream(), self.side, False
+        main = torch.cuda.current_stream()
+
+        def stream_of(tag):
+            if tag == 0:
+                return main
+            if tag not in self.streams:
+                self.streams[tag] = torch.cuda.Stream()
+            return self.streams[tag]
+
         for fn, args, tag in prog:
             if fn is FORK:
+                parent, children = args
                 ev = torch.cuda.Event()
-                ev.record(main)
-                side.wait_event(ev)
-                forked = True
+                ev.record(stream_of(parent))
+                for c in children:
+                    stream_of(c).wait_event(ev)
             elif fn is JOIN:
-                if forked:
+                parent, children = args
+                for c in children:
                     ev = torch.cuda.Event()
-                    ev.record(side)
-                    main.wait_event(ev)
-                    forked = False
-            elif tag == 1 and forked:
-                with torch.cuda.stream(side):
-                    fn(*args)
-            else:
+                    ev.record(stream_of(c))
+                    stream_of(parent).wait_event(ev)
+            elif tag == 0:
                 fn(*args)
-        if forked:
-            ev = torch.cuda.Event()
-            ev.record(side)
-            main.wait_event(ev)
+            else:
+                with torch.cuda.stream(stream_of(tag)):
+                    fn(*args)
 
 
 class Engine:
     def __init__(self, K, width=18, stage=1, skeleton="mpii", B=2, R=224, n_data=20000, nce_k=16384, nce_t=0.07,
                  nce_m=0.5, temperature=0.07, num_samples=400, feat_dim=128, world_size=1, train=True, use_tc=True,
-                 store=None, two_streams=True, fuse_bn_finalize=False):
+                 store=None, two_streams=True, fuse_bn_finalize=False, branch_streams=True):
         assert feat_dim == 128, "the NCE / loss kernels are specialised for feat_dim=128"
         assert R % 32 == 0, "HRNet needs the input side to be a multiple of 32"
         assert B >= 2, "the reference collapses B=1 (mem_bank.py:39 out.squeeze())"
@@ -237,6 +245,7 @@ class Engine:
         self.world = world_size
         self.two_streams = two_streams   # encoder2 on a side stream (see Plan)
         self.fuse_bn_finalize = fuse_bn_finalize     # see _bn_stats
+        self.branch_streams = branch_streams         # HR-module branches 1..3 on their own streams (see Plan)
         self.use_tc = use_tc     # tensor-core path for the stride-1 convs (SIMT fp32 implicit GEMM otherwise)
         self.ch = L.WIDTHS[width]
         self.cm = sum(self.ch)
@@ -264,9 +273,10 @@ class Engine:
         maxc = 4 * max(self.ch[-1], 256)
         # shared scratch (single stream => sequential reuse is safe)
         # scratch per stream tag (launches with the same tag are sequential, so reuse within a tag is safe)
-        self._part = [K.empty(2 * 4096 * 2 * 256) for _ in range(2)]
-        self._k = [(K.empty(maxc), K.empty(maxc), K.empty(maxc)) for _ in range(2)]
-        self._cnt = [K.zeros(4, dtype=torch.int32) for _ in range(2)]      # last-CTA tickets of the fused BN statistics kernels
+        ntags = 8          # 0 / 1: the encoders' own streams; 2-4 / 5-7: branches 1..3 of their HR modules
+        self._part = [K.empty(2 * 4096 * 2 * 256) for _ in range(ntags)]
+        self._k = [(K.empty(maxc), K.empty(maxc), K.empty(maxc)) for _ in range(ntags)]
+        self._cnt = [K.zeros(4, dtype=torch.int32) for _ in range(ntags)]  # last-CTA tickets of the fused BN statistics kernels
         # step inputs (static buffers; the caller copies each batch in)
         self.x = K.zeros(B, 6, R, R)
         self.skel = K.zeros(B, J, 2)
@@ -283,14 +293,14 @@ class Engine:
             xin = K.empty(B, R, R, 3)
             p.f(K.nchw_to_nhwc, self.x, xin, B, 6, R * R, 3 * m, 3)
             xs.append(Act(xin, B, R, R, 3, needs_grad=False))
-        p.mark_f(FORK)
+        p.fork(0, [1])
         self.feat1 = self._hrnet("encoder1.", xs[0])
         p.tag = 1
         # the skeleton encoder's launches are tiny (B*J rows): on the side stream they hide under encoder1's kernels
         self.feat3 = self._sgcn("encoder3.", self.skel)
         self.feat2 = self._hrnet("encoder2.", xs[1])
         p.tag = 0
-        p.mark_f(JOIN)
+        p.join(0, [1])
         self.f = K.empty(B, 384)
         self.df = K.zeros(B, 384)
         self._head("head1.0", self._pool(self.feat1), self.cm, 0)
@@ -552,10 +562,19 @@ class Engine:
         return out
 
     def _hr_module(self, xs, mp):
+        p = self.plan
         xs = list(xs)
+        base = p.tag                                           # 0 (encoder1) or 1 (encoder2)
+        children = [2 + 3 * base + (i - 1) for i in range(1, len(xs))] if self.branch_streams else []
+        if children:
+            p.fork(base, children)                             # the branches are independent until the fuse layers
         for i in range(len(xs)):
+            p.tag = children[i - 1] if (children and i > 0) else base
             for blk in range(4):
                 xs[i] = self._basic_block(xs[i], "%sbranches.%d.%d." % (mp, i, blk))
+        p.tag = base
+        if children:
+            p.join(base, children)
         return [self._fuse(xs, mp, i) for i in range(len(xs))]
 
     def _hrnet(self, pre, x):              # official_hrnet.py:411-454
@@ -984,7 +1003,7 @@ class Engine:
     @property
     def launches_per_step(self):
         """C-ABI calls in one step (each enqueues at least one kernel)."""
-        return len(self.plan.fwd) + len(self.plan.bwd) + 1 + 3 + 1
+        return sum(1 for e in self.plan.fwd + self.plan.bwd if e[0] is not FORK and e[0] is not JOIN) + 1 + 3 + 1
 
     def total_loss(self):
         n = 11 if self.stage == 2 else 6
