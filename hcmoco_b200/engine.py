@@ -141,12 +141,26 @@ class Plan:
         self.fwd, self.bwd, self._builders = [], [], []
         self.tag = 0
         self.streams = {}
+        self.off_path_streams = True
+        self._wtags = set()
 
     def f(self, fn, *args):
         self.fwd.append((fn, args, self.tag))
 
     def b(self, fn, *args):
         self.bwd.append((fn, args, self.tag))
+
+    def b_off_path(self, fn, *args):
+        """A backward launch nothing later in the program depends on (a weight gradient: it only feeds the flat gradient
+        buffer): it goes to the side stream `8 + tag`, ordered after what has been recorded on `tag` so far, and is joined at
+        the very end of the backward program.  The critical chain of a layer is then BN backward -> data gradient, and
+        the weight-gradient kernels fill the SMs and the gaps those leave."""
+        if not self.off_path_streams:
+            return self.b(fn, *args)
+        wtag = 8 + self.tag
+        self._wtags.add(wtag)
+        self.bwd.append((FORK, (self.tag, (wtag,)), self.tag))
+        self.bwd.append((fn, args, wtag))
 
     def fork(self, parent, children):
         children = tuple(children)
@@ -172,6 +186,8 @@ class Plan:
             bld()
         self.tag = 0
         self._builders = []
+        if self._wtags:
+            self.bwd.append((JOIN, (0, tuple(sorted(self._wtags))), 0))
         return n
 
     def grad(self, act):
@@ -232,7 +248,8 @@ class Plan:
 class Engine:
     def __init__(self, K, width=18, stage=1, skeleton="mpii", B=2, R=224, n_data=20000, nce_k=16384, nce_t=0.07,
                  nce_m=0.5, temperature=0.07, num_samples=400, feat_dim=128, world_size=1, train=True, use_tc=True,
-                 store=None, two_streams=True, fuse_bn_finalize=False, branch_streams=True):
+                 store=None, two_streams=True, fuse_bn_finalize=False, branch_streams=True,
+                 wgrad_streams=True):
         assert feat_dim == 128, "the NCE / loss kernels are specialised for feat_dim=128"
         assert R % 32 == 0, "HRNet needs the input side to be a multiple of 32"
         assert B >= 2, "the reference collapses B=1 (mem_bank.py:39 out.squeeze())"
@@ -246,6 +263,7 @@ class Engine:
         self.two_streams = two_streams   # encoder2 on a side stream (see Plan)
         self.fuse_bn_finalize = fuse_bn_finalize     # see _bn_stats
         self.branch_streams = branch_streams         # HR-module branches 1..3 on their own streams (see Plan)
+        self.wgrad_streams = wgrad_streams           # weight gradients off the critical path (Plan.b_off_path)
         self.use_tc = use_tc     # tensor-core path for the stride-1 convs (SIMT fp32 implicit GEMM otherwise)
         self.ch = L.WIDTHS[width]
         self.cm = sum(self.ch)
@@ -268,6 +286,7 @@ class Engine:
     def build(self):
         K, B, R, J = self.K, self.B, self.R, self.J
         self.plan = p = Plan(K)
+        p.off_path_streams = self.wgrad_streams
         self.pack_jobs = []
         p.f(self._run_packs)
         maxc = 4 * max(self.ch[-1], 256)
@@ -441,10 +460,11 @@ class Engine:
                 spec["g_out"], spec["g_acc"], P, cout)
             dy = spec["dy"]
             if self.use_tc and K.tc_wgrad_supported(B, H, W, cin, cout, ks, stride):
-                p.b(K.tc_wgrad, x.data, dy, st.grad(ck + ".weight"), 0, B, H, W, cin, cout, ks, stride, x.scale, x.shift, int(x.relu))
+                p.b_off_path(K.tc_wgrad, x.data, dy, st.grad(ck + ".weight"), 0, B, H, W, cin, cout, ks, stride, x.scale, x.shift,
+                             int(x.relu))
             else:
-                p.b(K.conv2d_wgrad, x.data, dy, st.grad(ck + ".weight"), B, H, W, cin, cout, ks, stride, x.scale, x.shift,
-                    int(x.relu))
+                p.b_off_path(K.conv2d_wgrad, x.data, dy, st.grad(ck + ".weight"), B, H, W, cin, cout, ks, stride, x.scale,
+                             x.shift, int(x.relu))
             if x.needs_grad:
                 if x.lazy:
                     assert x.consumers == 1 and x.grad is None
