@@ -242,10 +242,17 @@ def run_engine(a):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        pending = None
         for i in range(n):
-            step.run(batches[i % len(batches)])
+            # host batches: the next step's H2D copy is started on a copy stream before this step is enqueued, and every
+            # step's losses / accuracies are read back (D2H into pinned memory) one step later, so the host never idles the GPU
+            step.run(batches[i % len(batches)], next_batch=batches[(i + 1) % len(batches)] if read_back else None)
             if read_back:
-                step.results()               # D2H read of the step's losses / accuracies
+                if pending is not None:
+                    pending()
+                pending = step.results_async()
+        if pending is not None:
+            pending()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)

@@ -317,6 +317,7 @@ class ContrastTrainer(object):
         self.local_group = None
         self.logger = None
         self.graphs = {}
+        self.stagers = {}
 
     # ---- distributed environment (base_trainer.py:20-73).  torchrun / SLURM env; one process per GPU; NVSwitch makes the
     # per-node process groups of the reference (ShuffleBN only) unnecessary.
@@ -471,7 +472,16 @@ class ContrastTrainer(object):
         x = data[0]
         eng = model.engine_for(x.shape[0], x.shape[-1], contrast)
         dev = eng.x.device
-        eng.x.copy_(x, non_blocking=True)
+        if dev.type == "cuda" and not x.is_cuda and x.is_pinned():
+            # pinned loader batches: the H2D copy runs on a copy stream while the previous step (still executing: the loop only
+            # syncs every print_freq steps) computes; the step starts with a device-to-device copy
+            from .pretrain import InputStager
+            stager = self.stagers.get(id(eng))
+            if stager is None:
+                stager = self.stagers[id(eng)] = InputStager(eng.x)
+            stager.consume(stager.stage(x), eng.x)
+        else:
+            eng.x.copy_(x, non_blocking=True)
         eng.index.copy_(data[1], non_blocking=True)
         eng.skel.copy_(data[2], non_blocking=True)
         eng.joints_yx.copy_(data[4], non_blocking=True)

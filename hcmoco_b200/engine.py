@@ -1029,9 +1029,30 @@ class Engine:
         n = 11 if self.stage == 2 else 6
         return self.losses[:n].sum()
 
+    def results_async(self):
+        """Enqueue the D2H read of this step's losses / accuracies (32 floats into pinned memory) behind the step and return
+        a callable that waits for it and unpacks: a training loop calls it one step later, so the host never idles the GPU."""
+        if not hasattr(self, "_res_host"):
+            self._res_host = [torch.empty(32, pin_memory=True) for _ in range(2)]
+            self._res_slot = 0
+        host = self._res_host[self._res_slot]
+        self._res_slot ^= 1
+        host[:16].copy_(self.losses, non_blocking=True)
+        host[16:].copy_(self.accs, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+
+        def wait():
+            ev.synchronize()
+            return self._unpack(host.clone())
+
+        return wait
+
     def results(self):
         """Host copy of the step's losses and accuracies (one D2H read)."""
-        la = torch.cat([self.losses, self.accs]).cpu()
+        return self._unpack(torch.cat([self.losses, self.accs]).cpu())
+
+    def _unpack(self, la):
         ls, ac = la[:16], la[16:]
         out = dict(nce_losses=ls[0:6], nce_accs=ac[0:6])
         if self.stage == 2:
