@@ -224,6 +224,8 @@ def run_engine(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # keep stdout for the ONE JSON line: NCCL's version / debug lines (NCCL_DEBUG=VERSION|INFO in the environment) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K = CudaKernels()
     step = PretrainStep(K, width=a.width, stage=a.stage, B=a.batch, R=a.res, n_data=a.n_data, nce_k=a.nce_k,
