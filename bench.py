@@ -224,9 +224,20 @@ def run_engine(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        # keep stdout for the ONE JSON line: NCCL's version / debug lines (NCCL_DEBUG=VERSION|INFO in the environment) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # keep stdout for the ONE JSON line: NCCL prints its version (and, with NCCL_DEBUG=INFO, its topology) to stdout while
+        # the communicator is created — point fd 1 at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     K = CudaKernels()
     step = PretrainStep(K, width=a.width, stage=a.stage, B=a.batch, R=a.res, n_data=a.n_data, nce_k=a.nce_k,
                         world_size=world, rank=rank, use_graph=not a.no_graph, seed=0)
