@@ -152,13 +152,14 @@ def test_reference_surface_on_gpu(K, tmp_path):
     model.store.load_state_dict(P)
     ref = O.train_step(P, mom, banks, batch, nce, dense, width=cfg["width"], skeleton=cfg["skeleton"], stage=cfg["stage"],
                        first=True)
-    data = [batch["x"], batch["index"], batch["skeleton"], None, batch["joints_yx"], batch["joints_vis"], batch["use_depth"],
-            batch["depth_mask"], None]
+    # a pinned host batch, as a DataLoader(pin_memory=True) delivers it: the RGB-D tensor goes through the copy-stream stager
+    data = [batch["x"].pin_memory(), batch["index"], batch["skeleton"], None, batch["joints_yx"], batch["joints_vis"],
+            batch["use_depth"], batch["depth_mask"], None]
     mem.injected_idx = nce.cuda()
     trainer.injected_dense_idx = dense.cuda()
     res = trainer.train_step(model, mem, optimizer, data)()
     eng = model.engine_for(cfg["B"], cfg["R"])
-    assert hasattr(eng, "graph")
+    assert hasattr(eng, "graph") and id(eng) in trainer.stagers
     assert rel(res["loss"], ref["loss"]) < 1e-3 and rel(eng.f, ref["f"]) < 1e-3
     assert rel(res["dense_losses"], torch.stack(ref["dense_losses"])) < 1e-3
     for i in range(3):
