@@ -644,8 +644,6 @@ class Engine:
             bk = q + ".bn"
             scale, shift, mean, invstd = K.empty(cout), K.empty(cout), K.empty(cout), K.empty(cout)
             out = K.empty(B, J, cout)
-            nparts = K.colstat_rows(M, cout)
-            bf = st.buffers
             self._bn_stats(y, M, cout, bk, BN1D_MOMENTUM, scale, shift, mean, invstd)
             p.f(K.bn_apply, y, scale, shift, None, None, None, 1, out, M, cout)
         else:
