@@ -40,6 +40,14 @@ def test_host_side_queries(lib):
         assert lib.hcm_tc_conv_supported(64, H, H, Cin, Cout, ks, stride) == 1, (H, Cin, Cout, ks, stride)
         assert lib.hcm_tc_wgrad_supported(64, H, H, Cin, Cout, ks, stride) == 1, (H, Cin, Cout, ks, stride)
         assert lib.hcm_tc_conv_wpack_bytes(64, H, H, Cin, Cout, ks) >= Cin * Cout * ks * ks * 4   # hi + lo bf16, padded
+    # configs[4] (HRNet-w32, 384x384, B=16 per GPU): every layer but the 3-channel stem runs on the tensor-core kernels
+    for (H, Cin, Cout, ks, stride) in [(96, 32, 32, 3, 1), (48, 64, 64, 3, 1), (24, 128, 128, 3, 1), (12, 256, 256, 3, 1),
+                                       (96, 64, 256, 1, 1), (96, 256, 32, 3, 1), (96, 256, 64, 3, 2), (192, 64, 64, 3, 2),
+                                       (12, 256, 32, 1, 1), (96, 32, 128, 1, 1), (12, 256, 128, 1, 1)]:
+        assert lib.hcm_tc_conv_supported(16, H, H, Cin, Cout, ks, stride) == 1, (H, Cin, Cout, ks, stride)
+        assert lib.hcm_tc_wgrad_supported(16, H, H, Cin, Cout, ks, stride) == 1, (H, Cin, Cout, ks, stride)
+        if stride == 2:
+            assert lib.hcm_tc_dgrad_s2_supported(16, H, H, Cin, Cout) == 1
     assert lib.hcm_tc_conv_supported(64, 256, 256, 3, 64, 3, 2) == 0          # odd channel count: SIMT stem kernel instead
     assert lib.hcm_tc_conv_supported(2, 15, 15, 18, 18, 3, 2) == 0            # stride 2 needs even H, W
     assert lib.hcm_tc_conv_supported(2, 16, 16, 18, 18, 5, 1) == 0
