@@ -7,9 +7,16 @@
 Workload at N=1: BASELINE.json configs[1] — first-stage sample-level NCE, HRNet-w18 x2 + SemGCN, 256x256,
 per-GPU batch 64, K=16384 negatives, bank of 165 894 rows (weak scaling: every rank runs that batch).
 A "step" = forward + six NCE losses + backward + memory-bank update + SGD, on synthetic triplets.
-Prints ONE JSON line (rank 0).
+Prints ONE JSON line (rank 0).  Besides the contract keys the line carries
+  roofline            the dominant kernel (median of 5 warmed, event-timed passes inside a real step)
+  roofline_other      the conv family, the north-star KPI kernels (stage-4 conv, dense affinity), the NCE kernels
+  extra_configs       the second-stage / w32 configurations of BASELINE.json (configs[2..4], per-GPU shapes) timed the same way
+  gpu_eager_baseline  the reference ALGORITHM (oracle statement) under PyTorch eager + cuDNN on this GPU, TF32 on / off
+                      ("the existing Blackwell library path")
+  cpu_baseline        the same algorithm on the host cores
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -24,6 +31,7 @@ import torch  # noqa: E402
 
 METRIC = "pretrain_triplets_per_sec"
 UNIT = "triplets/s"
+DOMINANT = "tc_conv 64x64 18->18 k3 s1"       # fallback name only; the kernel is picked by median time (see run_engine)
 
 
 def parse():
@@ -36,10 +44,13 @@ def parse():
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--width", type=int, default=18)
     ap.add_argument("--stage", type=int, default=1)
+    ap.add_argument("--skeleton", default="mpii")
     ap.add_argument("--n-data", type=int, default=165894)
     ap.add_argument("--nce-k", type=int, default=16384)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs legs (configs[2..4])")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: after the warm-up run ONE step between cudaProfilerStart/Stop and exit "
                          "(use with `ncu --profile-from-start off`); prints no bench line")
@@ -53,12 +64,17 @@ def workload_name(a):
         a.stage, a.width, a.res, a.res, a.batch, a.nce_k, a.n_data)
 
 
+def config_of(a, world):
+    """The `config` object: identical for the engine arm and the reference arm (the driver compares them)."""
+    return {"workload": workload_name(a), "global_batch": a.batch * world, "parallelism": "dp%d" % world,
+            "l2": "working set per step (tens of GB of activations) exceeds the 126 MB L2; no flush needed"}
+
+
 # ------------------------------------------------------------------------------------------ FLOP / byte model
 def conv_flops_per_image(width, R):
     """Useful conv FLOPs (2*MAC) of ONE HRNet forward on one R x R image, from the layer list itself."""
     from hcmoco_b200 import layout as L
     keys = L.model_keys(width, 1, "mpii")
-    ch = L.WIDTHS[width]
     total = 0
 
     def res_of(k):
@@ -132,44 +148,81 @@ class Clocks:
                 "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------ reference arm (CPU)
-def cpu_reference_steps(a, steps, warmup, batch):
-    """The reference algorithm (oracle restatement, fp32, all host threads) on a bounded sample of the
-    workload: same model, resolution, K and bank, `batch` triplets per step."""
+# ------------------------------------------------------------------------------------------ the reference algorithm (oracle)
+def _oracle_problem(a, batch, device="cpu"):
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     from oracle import hcmoco_oracle as O
     from synth import synthetic_banks, synthetic_state
     from hcmoco_b200.synthetic import make_batch, make_dense_idx, make_nce_idx
+    J = 16 if a.skeleton == "mpii" else 13
+    layout = O.model_layout(a.width, a.stage, a.skeleton)
+    P = synthetic_state(layout, 0)
+    P = type(P)((k, v.to(device)) for k, v in P.items())
+    mom = O.make_momentum(P)
+    banks = [b.to(device) for b in synthetic_banks(a.n_data, 128, 0)]
+    d = make_batch(batch, a.res, J, a.n_data, seed=1234)
+    bt = dict(x=d[0], index=d[1], skeleton=d[2], joints_yx=d[4], joints_vis=d[5], use_depth=d[6], depth_mask=d[7])
+    nce = make_nce_idx(batch, a.nce_k, a.n_data, d[1]).to(device)
+    dense = make_dense_idx(d[7], a.res // 4, 400).to(device)
+    bt = {k: v.to(device) for k, v in bt.items()}
+
+    def step(first):
+        return O.train_step(P, mom, banks, bt, nce, dense, width=a.width, skeleton=a.skeleton, stage=a.stage, first=first)
+
+    return step
+
+
+def cpu_reference_steps(a, steps, warmup, batch):
+    """The reference algorithm (oracle restatement, fp32, all host threads) on a bounded sample of the
+    workload: same model, resolution, K and bank, `batch` triplets per step."""
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    layout = O.model_layout(a.width, a.stage, "mpii")
-    P = synthetic_state(layout, 0)
-    mom = O.make_momentum(P)
-    banks = synthetic_banks(a.n_data, 128, 0)
-    d = make_batch(batch, a.res, 16, a.n_data, seed=1234)
-    bt = dict(x=d[0], index=d[1], skeleton=d[2], joints_yx=d[4], joints_vis=d[5], use_depth=d[6], depth_mask=d[7])
-    nce = make_nce_idx(batch, a.nce_k, a.n_data, d[1])
-    dense = make_dense_idx(d[7], a.res // 4, 400)
+    step = _oracle_problem(a, batch)
     times = []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
-        O.train_step(P, mom, banks, bt, nce, dense, width=a.width, stage=a.stage, first=(s == 0))
+        step(s == 0)
         times.append(time.perf_counter() - t0)
     t = sum(times[warmup:]) / max(1, steps)
     return batch / t, t, cores
+
+
+def gpu_eager_steps(a, batch, tf32, steps=5, warmup=3):
+    """The same algorithm statement under PyTorch eager on THIS GPU: cuDNN convolutions / batch-norm, cuBLAS, ATen, fp32 tensors,
+    `cudnn.benchmark=True` as the reference sets it (learning/base_trainer.py:28); tf32=True is PyTorch's shipped cuDNN default
+    (the reference as a user runs it), tf32=False is the fp32-exact mode the parity bar is stated in."""
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = bool(tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+    step = _oracle_problem(a, batch, "cuda")
+    for s in range(warmup):
+        step(s == 0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+        step(False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del step
+    gc.collect()
+    torch.cuda.empty_cache()
+    return {"value": batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": batch, "steps": steps, "warmup": warmup}
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = min(a.steps, 5), min(a.warmup, 1)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = a.steps, a.warmup
     val, t, cores = cpu_reference_steps(a, steps, warmup, a.cpu_batch)
-    sample = "%d timed steps of %d triplets (same model/resolution/K/bank as the workload), %d warm-up" % (
-        steps, a.cpu_batch, warmup)
+    sample = "each step = %d triplets of the workload (same model/resolution/K/bank), %d timed steps, %d warm-up" % (
+        a.cpu_batch, steps, warmup)
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
            "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a), "sample": sample},
+           "dtype": "f32", "data": "synthetic", "config": config_of(a, world),
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -189,9 +242,9 @@ def dense_affinity_roofline(K, hbm_peak, B=32, h=64, S=400, reps=20):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2: evict the maps between launches
     out = {}
     for name, fn in (("dense_affinity_fwd", lambda: K.dense_affinity_fwd(G1, G2, pix, kept, use_depth, B, S, h, 128, 1 / 0.07, stat, fin)),
-                     ("dense_affinity_bwd", lambda: K.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1 / 0.07, 1.0, d1, d2))):
+                     ("dense_affinity_bwd", lambda: K.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1 / 0.07, 1.0, 1.0, d1, d2))):
         fn()
-        ms = 0.0
+        ts = []
         for _ in range(reps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -199,25 +252,103 @@ def dense_affinity_roofline(K, hbm_peak, B=32, h=64, S=400, reps=20):
             fn()
             e1.record()
             torch.cuda.synchronize()
-            ms += e0.elapsed_time(e1)
-        ms /= reps
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        ms = ts[len(ts) // 2]
         nbytes = B * 2 * S * 128 * 4
         flops = 2.0 * B * 2 * S * S * 128 * (1 if name.endswith("fwd") else 2)      # both L and L^T strips (+ dX = G*Y)
         out[name] = {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": nbytes, "us_per_launch": ms * 1e3,
                      "useful_tflops": flops / (ms * 1e-3) / 1e12,
                      "shape": "B=%d depth-bearing triplets, %dx%d maps, S=%d, L2 flushed between launches" % (B, h, h, S),
-                     "note": "AI = S/4 = 100 FLOP/B (x2 for both softmax directions): the 3-pass split-bf16 contraction and the "
+                     "note": "AI = S/4 = 100 FLOP/B (x2 for both softmax directions): the split-bf16 contraction and the "
                              "exp-heavy epilogue bound it, not HBM (DESIGN.md 3.2)"}
+    del flush
     return out
 
 
 # ------------------------------------------------------------------------------------------ engine arm
+class Runner:
+    """One PretrainStep + its synthetic batches; `timed()` is the contract's timed region."""
+
+    def __init__(self, a, K, world, rank, dist):
+        from hcmoco_b200.pretrain import PretrainStep
+        from hcmoco_b200.synthetic import make_batch
+        self.a, self.world, self.dist = a, world, dist
+        J = 16 if a.skeleton == "mpii" else 13
+        self.step = PretrainStep(K, width=a.width, stage=a.stage, skeleton=a.skeleton, B=a.batch, R=a.res, n_data=a.n_data,
+                                 nce_k=a.nce_k, world_size=world, rank=rank, use_graph=not a.no_graph, seed=0)
+        # synthetic triplets: 2 distinct host batches in pinned memory (e2e) and their device copies (device arm)
+        self.host = [make_batch(a.batch, a.res, J, a.n_data, seed=1234 + rank + 17 * i, pin=True) for i in range(2)]
+        self.dev = [[t.cuda(non_blocking=True) for t in b] for b in self.host]
+        torch.cuda.synchronize()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, batches, n, read_back):
+        step = self.step
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pending = None
+        for i in range(n):
+            # host batches: the next step's H2D copies are started on a copy stream before this step is enqueued, and every
+            # step's losses / accuracies are read back (D2H into pinned memory) one step later, so the host never idles the GPU
+            step.run(batches[i % len(batches)], next_batch=batches[(i + 1) % len(batches)] if read_back else None)
+            if read_back:
+                if pending is not None:
+                    pending()
+                pending = step.results_async()
+        if pending is not None:
+            pending()
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    def measure(self, steps, warmup):
+        a = self.a
+        for i in range(warmup):
+            self.step.run(self.dev[i % 2])
+        ms_dev = self.timed(self.dev, steps, False)
+        self.step.run(self.host[0], next_batch=self.host[0])       # e2e warm-up: stager buffers, pinned result slots
+        ms_e2e = self.timed(self.host, steps, True)
+        h2d = self.step.h2d_bytes(self.host[0])
+        return {"value": a.batch * self.world * steps / (ms_dev / 1e3), "ms_per_step": ms_dev / steps,
+                "e2e": {"value": a.batch * self.world * steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 32 * 4, "ms_per_step": ms_e2e / steps},
+                "gpu_launches": self.step.launches_per_step * steps}
+
+    def close(self):
+        self.step = self.host = self.dev = None
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
+def replicas_identical(step, dist, world):
+    """Every rank must hold bit-identical parameters, momentum and memory banks after the timed steps (SURVEY.md 8(e);
+    contrast_trainer.py:578-579, mem_bank.py:195-199): all-gather an integer checksum of each and compare."""
+    e = step.eng
+    sums = []
+    for t in (e.store.p, e.store.m, e.banks[0], e.banks[1], e.banks[2]):
+        v = t.view(torch.int32).to(torch.int64)
+        sums += [v.sum(), (v * (torch.arange(v.numel(), device=v.device) % 8191 + 1)).sum()]
+    mine = torch.stack(sums)
+    allv = torch.empty(world, mine.numel(), dtype=torch.int64, device="cuda")
+    dist.all_gather_into_tensor(allv, mine)
+    return bool((allv == allv[0:1]).all())
+
+
 def run_engine(a):
     import torch.distributed as dist
     from hcmoco_b200.kernels import CudaKernels
-    from hcmoco_b200.pretrain import PretrainStep
-    from hcmoco_b200.synthetic import make_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -239,71 +370,46 @@ def run_engine(a):
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     K = CudaKernels()
-    step = PretrainStep(K, width=a.width, stage=a.stage, B=a.batch, R=a.res, n_data=a.n_data, nce_k=a.nce_k,
-                        world_size=world, rank=rank, use_graph=not a.no_graph, seed=0)
-    # synthetic triplets: 2 distinct host batches in pinned memory (e2e) and their device copies (device arm)
-    host = [make_batch(a.batch, a.res, 16, a.n_data, seed=1234 + rank + 17 * i, pin=True) for i in range(2)]
-    dev = [[t.cuda(non_blocking=True) for t in b] for b in host]
-    torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(batches, n, read_back):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        pending = None
-        for i in range(n):
-            # host batches: the next step's H2D copy is started on a copy stream before this step is enqueued, and every
-            # step's losses / accuracies are read back (D2H into pinned memory) one step later, so the host never idles the GPU
-            step.run(batches[i % len(batches)], next_batch=batches[(i + 1) % len(batches)] if read_back else None)
-            if read_back:
-                if pending is not None:
-                    pending()
-                pending = step.results_async()
-        if pending is not None:
-            pending()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms
-
-    for i in range(a.warmup):
-        step.run(dev[i % 2])
+    run = Runner(a, K, world, rank, dist)
+    step = run.step
     if a.ncu_step:
+        for i in range(a.warmup):
+            step.run(run.dev[i % 2])
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        step.run(dev[0])
+        step.run(run.dev[0])
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
-    calls0 = K.launches
-    ms_dev = timed(dev, a.steps, False)
-    launches = step.launches_per_step * a.steps
-    ms_e2e = timed(host, a.steps, True)
+    main = run.measure(a.steps, a.warmup)
     clk = clocks.stop() if rank == 0 else None
-    h2d = sum(t.numel() * t.element_size() for i, t in enumerate(host[0]) if i in (0, 1, 2, 4, 5, 6, 7))
-    d2h = 32 * 4
-    # per-kernel-family device time inside one real step (events around every C-ABI launch, no graph)
-    fam = step.profile_families(dev[0])
+    identical = replicas_identical(step, dist, world) if world > 1 else None
+    # per-kernel-family device time inside one real step (events around every C-ABI launch, no graph): 5 warmed passes,
+    # per-shape MEDIAN (one pass is noisy: a host hiccup between two event records lands in whatever kernel it hits)
+    fams, details = [], []
+    for _ in range(5):
+        fams.append(step.profile_families(run.dev[0]))
+        details.append(step.detail)
+
+    def med(rows, key):
+        v = sorted(r[key]["ms"] for r in rows if key in r)
+        return v[len(v) // 2]
+
+    fam = {k: {"ms": med(fams, k), "calls": fams[0][k]["calls"]} for k in fams[0]}
+    detail = {k: {"ms": med(details, k), "calls": details[0][k]["calls"]} for k in details[0]}
     if a.detail and rank == 0:
         with open(a.detail, "w") as f:
-            for k, v in sorted(step.detail.items(), key=lambda kv: -kv[1]["ms"]):
+            for k, v in sorted(detail.items(), key=lambda kv: -kv[1]["ms"]):
                 f.write("%9.3f ms %4d calls %8.1f us/call  %s\n" % (v["ms"], v["calls"], 1e3 * v["ms"] / v["calls"], k))
-    step_ms = ms_dev / a.steps
-    value = a.batch * world * a.steps / (ms_dev / 1e3)
-    e2e = a.batch * world * a.steps / (ms_e2e / 1e3)
+    step_ms = main["ms_per_step"]
     if rank != 0:
+        run.close()
+        extra_configs(a, K, world, rank, dist)        # every rank takes part in the collective legs
+        if world > 1:
+            dist.destroy_process_group()
         return
     peaks = {}
     try:
@@ -318,8 +424,8 @@ def run_engine(a):
     conv_names = ("conv2d", "tc_conv", "tc_wgrad", "tc_dgrad", "_run_packs", "tc_pack")   # conv kernels + their weight packing
     conv_ms = sum(v["ms"] for k, v in fam.items() if k.startswith(conv_names))
     tot_ms = sum(v["ms"] for v in fam.values())
-    # ---- roofline of the DOMINANT KERNEL: the (kernel, shape) with the largest summed device time inside one real step
-    dom_shape, dom = max(step.detail.items(), key=lambda kv: kv[1]["ms"])
+    # ---- roofline of the DOMINANT KERNEL: the (kernel, shape) with the largest summed median device time inside one real step
+    dom_shape, dom = max(detail.items(), key=lambda kv: kv[1]["ms"])
     parts = dom_shape.split()                            # e.g. "tc_conv 64x64 18->18 k3 s1"
     hh, ww = [int(v) for v in parts[1].split("x")]
     cin, cout = [int(v) for v in parts[2].split("->")]
@@ -342,6 +448,7 @@ def run_engine(a):
             "traffic": None if tr is None else tr["dram_bytes"],
             "traffic_source": None if tr is None else tr["source"],
             "peak_source": peak_src + (", copy bandwidth" if hbm_bound else ", bf16 dense sustained"),
+            "timing": "median over 5 warmed passes of CUDA events around every launch of this shape inside a real step",
             "arithmetic_intensity_flop_per_byte": dom_flops / dom_bytes, "ridge_flop_per_byte": ridge,
             "algorithmic_bytes_per_launch": dom_bytes, "algorithmic_flops_per_launch": dom_flops,
             "us_per_launch": dom_us, "share_of_step": dom["ms"] / tot_ms,
@@ -355,7 +462,7 @@ def run_engine(a):
     # north-star KPI kernel 1: the widest stage-4 conv (3x3, C4 -> C4 at R/32)
     from hcmoco_b200 import layout as L
     c4, r32 = L.WIDTHS[a.width][-1], a.res // 32
-    kpi = step.detail.get("tc_conv %dx%d %d->%d k3 s1" % (r32, r32, c4, c4))
+    kpi = detail.get("tc_conv %dx%d %d->%d k3 s1" % (r32, r32, c4, c4))
     if kpi:
         us = 1e3 * kpi["ms"] / kpi["calls"]
         fl = 2.0 * a.batch * r32 * r32 * c4 * c4 * 9
@@ -373,18 +480,35 @@ def run_engine(a):
                            "traffic": None if tr is None else tr["dram_bytes"]}
     # north-star KPI kernel 2: the fused dense-affinity kernels on the second-stage per-GPU shape (B=32, 64x64 maps, S=400)
     other.update(dense_affinity_roofline(K, hbm_peak))
-    nce = other
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+    cfg = config_of(a, world)
+    cfg["cuda_graph"] = not a.no_graph
+    out = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic",
-           "config": {"workload": workload_name(a), "global_batch": a.batch * world, "parallelism": "dp%d" % world,
-                      "l2": "working set per step (tens of GB of activations) exceeds the 126 MB L2; no flush needed",
-                      "cuda_graph": not a.no_graph},
-           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "ms_per_step": ms_e2e / a.steps},
-           "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_other": nce,
+           "data": "synthetic", "config": cfg, "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "clocks": clk,
+           "roofline": roof, "roofline_other": other,
            "kernel_families_ms": {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
            "kernel_families_calls": {k: v["calls"] for k, v in fam.items()}}
+    if identical is not None:
+        out["replicas_identical"] = identical
+    run.close()
+    step = run = None
+    ex = extra_configs(a, K, world, rank, dist)
+    if ex:
+        out["extra_configs"] = ex
+    if not a.no_gpu_eager and world == 1:
+        eager = {}
+        for name, tf32 in (("tf32_on", True), ("tf32_off", False)):
+            try:
+                eager[name] = gpu_eager_steps(a, a.batch, tf32)
+            except Exception as ex_:          # never lose the bench line to the baseline leg
+                eager[name] = {"error": repr(ex_)[:200]}
+                gc.collect()
+                torch.cuda.empty_cache()
+        eager["what"] = ("the reference algorithm (oracle statement: F.conv2d / F.batch_norm / autograd / index_select + bmm) "
+                         "under PyTorch %s eager on this GPU, fp32 tensors, cudnn.benchmark=True, same batch and shapes as the "
+                         "workload; tf32_on = PyTorch's default cuDNN TF32 convolutions (misses the 1e-3 parity bar, SURVEY F8), "
+                         "tf32_off = fp32-exact" % torch.__version__)
+        out["gpu_eager_baseline"] = eager
     if not a.no_cpu_baseline and world == 1:
         val, t, cores = cpu_reference_steps(a, 3, 1, a.cpu_batch)
         out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
@@ -393,6 +517,34 @@ def run_engine(a):
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def extra_configs(a, K, world, rank, dist):
+    """BASELINE.json configs[2..4] at their per-GPU shapes (8-GPU global batches 256 / 256 / 128): the second-stage objectives
+    (dense + sparse + SCL, the 1x1 projections) and every HRNet-w32 / 384x384 shape, timed like the main workload."""
+    if a.no_extra or (a.stage, a.width, a.res, a.batch) != (1, 18, 256, 64):
+        return None
+    out = {}
+    for name, kw in (("C3_configs[2]", dict(stage=2, width=18, res=256, batch=32, skeleton="mpii")),
+                     ("C4_configs[3]", dict(stage=2, width=18, res=256, batch=32, skeleton="coco_reduce")),
+                     ("C5_configs[4]", dict(stage=2, width=32, res=384, batch=16, skeleton="mpii"))):
+        b = argparse.Namespace(**vars(a))
+        for k, v in kw.items():
+            setattr(b, k, v)
+        steps = max(3, min(a.steps, 10))
+        try:
+            r = Runner(b, K, world, rank, dist)
+            m = r.measure(steps, 3)
+            r.close()
+            r = None
+            m.update(workload=workload_name(b) + ", J=%d" % (16 if b.skeleton == "mpii" else 13), steps=steps, warmup=3,
+                     unit=UNIT, n_gpus=world)
+            out[name] = m
+        except Exception as ex_:
+            out[name] = {"error": repr(ex_)[:300]}
+            gc.collect()
+            torch.cuda.empty_cache()
+    return out if rank == 0 else None
 
 
 if __name__ == "__main__":

@@ -72,7 +72,12 @@ class _ModelFn(torch.autograd.Function):
         eng.seed_output_grads(gf, gouts[0] if len(gouts) > 0 else None,
                               gouts[1] if len(gouts) > 1 else None, gouts[2] if len(gouts) > 2 else None)
         eng.backward_model()
-        grads = tuple(model.store.view(model.store.g, k).view(model.store.keys[k]) for k in model.param_keys)
+        # hand autograd views of a COPY of the flat gradient buffer (one device-to-device copy): AccumulateGrad keeps the
+        # tensors it is given as `p.grad`, and the engine rewrites `store.g` on the next backward — aliasing the two would
+        # double the gradient from the second `zero_grad(set_to_none=False); backward()` on
+        st = model.store
+        flat = st.g.clone()
+        grads = tuple(st.view(flat, k).view(st.keys[k]) for k in model.param_keys)
         return (None, None, None, None) + grads
 
 
@@ -198,9 +203,16 @@ class _NceFn(torch.autograd.Function):
         mem, x, idx = ctx.mem, ctx.x, ctx.idx
         K, B, K1 = mem.K_, x.shape[0], idx.shape[1]
         df = K.zeros(B, 384)
+        banks = (mem.memory_1, mem.memory_2, mem.memory_3)
+        # swap the pre-update rows back in for the re-gather (see HCMoCoMem.forward), then restore the updated ones
+        cur = [b.index_select(0, mem.touched) for b in banks]
+        for b, old in zip(banks, mem.old_rows):
+            b.index_copy_(0, mem.touched, old)
         # lse = None: `logits` carries d(loss)/d(logits) itself
-        K.nce_bwd(mem.old_1, mem.old_2, mem.old_3, x[:, 0:128], x[:, 128:256], x[:, 256:384], 384, idx, B, K1, 128, mem.T,
+        K.nce_bwd(banks[0], banks[1], banks[2], x[:, 0:128], x[:, 128:256], x[:, 256:384], 384, idx, B, K1, 128, mem.T,
                   dlogits.contiguous(), None, None, 1.0, df, 384)
+        for b, c in zip(banks, cur):
+            b.index_copy_(0, mem.touched, c)
         return None, df, None
 
 
@@ -241,14 +253,16 @@ class HCMoCoMem(nn.Module):
         assert bsz >= 2, "the reference collapses bsz=1 (mem_bank.py:39 out.squeeze())"
         idx = self.draw(bsz, y)
         x = torch.cat((x1, x2, x3), 1)
-        # the backward re-gathers bank rows: keep the pre-update rows it needs (the touched rows only change after this call
-        # in the reference as well, but autograd there holds the gathered copies)
-        self.old_1, self.old_2, self.old_3 = self.memory_1.clone(), self.memory_2.clone(), self.memory_3.clone()
         logits = _NceFn.apply(self, x, idx)
         if all_x1 is not None and all_x2 is not None and all_x3 is not None and all_y is not None:
-            self.update(torch.cat((all_x1, all_x2, all_x3), 1).detach().contiguous(), all_y)
+            ux, uy = torch.cat((all_x1, all_x2, all_x3), 1).detach().contiguous(), all_y
         else:
-            self.update(x.detach().contiguous(), y)
+            ux, uy = x.detach().contiguous(), y
+        # the backward re-gathers bank rows and must see them as they were when the logits were computed (autograd in the
+        # reference holds the gathered copies): keep the pre-update contents of the few rows the update touches
+        self.touched = uy.clone()
+        self.old_rows = [getattr(self, "memory_%d" % i).index_select(0, uy) for i in (1, 2, 3)]
+        self.update(ux, uy)
         labels = torch.zeros(bsz, dtype=torch.long, device=x.device)
         return (logits[0], logits[1], logits[2], logits[3], logits[4], logits[5], labels)
 
@@ -278,14 +292,54 @@ class FusedSGD(torch.optim.Optimizer):
         g = optimizer.param_groups[0]
         return cls(model, g["lr"], g.get("momentum", 0.0), g.get("weight_decay", 0.0))
 
-    def zero_grad(self, set_to_none=False):
+    def zero_grad(self, set_to_none=True):
+        """torch.optim.Optimizer.zero_grad semantics for `p.grad` (the autograd path), plus the engine's flat buffer."""
         st = self.model.store
         self.model.K.zero(st.g, st.n * st.g.element_size())
+        flat = self._autograd_flat()
+        for p in self.param_groups[0]["params"]:
+            if p.grad is not None:
+                if set_to_none:
+                    p.grad = None
+                elif flat is None:
+                    p.grad.zero_()
+        if flat is not None and not set_to_none:
+            flat.zero_()
+
+    def _autograd_flat(self):
+        """The flat tensor all `p.grad`s are views of, in store layout (what `_ModelFn.backward` hands to autograd), or None."""
+        st, ps = self.model.store, self.param_groups[0]["params"]
+        g0 = ps[0].grad
+        if g0 is None or g0._base is None:
+            return None
+        base = g0._base
+        if base.numel() != st.n or base.dtype != st.g.dtype:
+            return None
+        es = base.element_size()
+        for k, p in zip(self.model.param_keys, ps):
+            if p.grad is None or p.grad._base is not base or p.grad.data_ptr() != base.data_ptr() + st.off[k][0] * es:
+                return None
+        return base
 
     @torch.no_grad()
-    def step(self, closure=None, gscale=1.0):
+    def step(self, closure=None, gscale=1.0, from_autograd=None):
+        """One fused launch.  The trainer's fused step leaves the gradient in `store.g` (from_autograd=False); after a
+        `loss.backward()` through `model(...)` the gradients live in `p.grad` (from_autograd=True; default: decided by
+        whether any `p.grad` is set) — views of one flat tensor in the common case, gathered per key otherwise."""
         g, st = self.param_groups[0], self.model.store
-        self.model.K.sgd_step(st.p, st.g, st.m, st.n, g["lr"], g["momentum"], g["weight_decay"], 0, gscale)
+        ps = self.param_groups[0]["params"]
+        if from_autograd is None:
+            from_autograd = any(p.grad is not None for p in ps)
+        src = st.g
+        if from_autograd:
+            flat = self._autograd_flat()
+            if flat is not None:
+                src = flat
+            else:
+                for k, p in zip(self.model.param_keys, ps):
+                    v = st.view(st.g, k)
+                    v.zero_() if p.grad is None else v.copy_(p.grad.reshape(-1))
+        self.model.K.sgd_step(st.p, src, st.m, st.n, g["lr"], g["momentum"], g["weight_decay"], 0, gscale)
 
     def load_state_dict(self, sd):
         st = self.model.store
@@ -331,11 +385,18 @@ class ContrastTrainer(object):
         if torch.cuda.is_available():
             torch.cuda.set_device(local)
         if world > 1 and not dist.is_initialized():
+            if "MASTER_ADDR" not in env and "SLURM_NODELIST" in env:
+                # base_trainer.py:36-44: first host of the SLURM allocation (multi-node srun launches)
+                import subprocess
+                addr = subprocess.getoutput("scontrol show hostname {} | head -n1".format(env["SLURM_NODELIST"])).strip()
+                env["MASTER_ADDR"] = addr if addr and " " not in addr else env["SLURM_NODELIST"].split(",")[0]
             env.setdefault("MASTER_ADDR", "127.0.0.1")
             env.setdefault("MASTER_PORT", "29500")
             dist.init_process_group(backend=getattr(a, "dist_backend", "nccl") if torch.cuda.is_available() else "gloo",
                                     rank=rank, world_size=world)
-        a.gpu, a.rank, a.local_rank, a.world_size, a.ngpus_per_node = local, rank, local, world, ngpus_per_node
+        # as the reference (base_trainer.py:40-47: local_rank = rank = SLURM_PROCID): `local_rank` is the GLOBAL rank, so that
+        # `save()` (gated on local_rank == 0, contrast_trainer.py:120) writes once per job, not once per node
+        a.gpu, a.rank, a.local_rank, a.world_size, a.ngpus_per_node = local, rank, rank, world, ngpus_per_node
         a.distributed = world > 1
 
     def wrap_up(self, model, model_ema, optimizer):
@@ -510,19 +571,12 @@ class ContrastTrainer(object):
             h.wait()
         else:
             eng.update_banks()
-        optimizer.step(gscale=1.0 / world)
+        optimizer.step(gscale=1.0 / world, from_autograd=False)
         return eng.results
 
-    # ---- the three objectives with the reference signatures (contrast_trainer.py:642, 744, 830).  Inputs are the
-    # NCHW tensors the reference passes; they run the same loss kernels the fused step uses (forward values; the
-    # trainer's fused program is what differentiates them).
-    def _loss_engine(self, feat_map1):
-        B, C, h, w = feat_map1.shape
-        key = ("loss", B, h)
-        if key not in self.graphs:
-            self.graphs[key] = None
-        return B, h
-
+    # ---- the three objectives with the reference signatures (contrast_trainer.py:642, 744, 830).  Inputs are the NCHW
+    # tensors the reference passes; outputs are ([loss tensors], [accuracy tensors]) that back-propagate into feat_map1 /
+    # feat_map2 / skeleton_map through the same loss kernels the fused step uses (hcmoco_b200/losses_api.py).
     def _compute_soft_pri3d_loss_accuracy(self, feat_map1, feat_map2, depth, criterion=None, use_depth=None, depth_mask=None,
                                           scale=None, sample_idx=None, K=None):
         from .losses_api import dense_loss

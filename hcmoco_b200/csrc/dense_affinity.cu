@@ -58,7 +58,7 @@ struct DaParams {
   const long long* pix; const float* kept; const float* fin;
   float* stat;                     // [B][2][S][4] = (lse, Z, sum w*logit, first-argmax hit)
   float* dG1; float* dG2;
-  float inv_T, gscale;
+  float inv_T, gscale, gscale_o;     // gscale: d(total)/d(loss_r2d), gscale_o: d(total)/d(loss_d2r)
   DaGeo g;
 };
 
@@ -115,11 +115,13 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
   const DaGeo& g = p.g;
   const int b = blockIdx.z, side = blockIdx.y, strip = blockIdx.x;
   if (p.kept[b] == 0.f) return;
-  float coef = 0.f;
+  // side 0 strips hold the statistics of loss_r2d (columns of L), side 1 those of loss_d2r: `own` / `other` swap with the side
+  float coef = 0.f, coef_o = 0.f;
   if (BWD) {
     const float nk = p.fin[4];
     if (!(nk > 0.f)) return;
-    coef = p.gscale / (nk * (float)g.S);
+    coef = (side == 0 ? p.gscale : p.gscale_o) / (nk * (float)g.S);
+    coef_o = (side == 0 ? p.gscale_o : p.gscale) / (nk * (float)g.S);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = g.S;
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
             const float l = v[i] * p.inv_T;
             const float dy = s_cy[q] - my_y, dx = s_cx[q] - my_x;
             const float w = __expf(-sqrtf(dy * dy + dx * dx));
-            gg = coef * (__expf(l - lse_own) + __expf(l - s_lse_o[q]) - w * (zinv_own + s_zinv_o[q]));
+            gg = coef * (__expf(l - lse_own) - w * zinv_own) + coef_o * (__expf(l - s_lse_o[q]) - w * s_zinv_o[q]);
           }
           gv[i] = gg;
         }
@@ -382,13 +384,13 @@ int hcm_dense_affinity_fwd(const float* G1, const float* G2, const long long* pi
 
 // dG1, dG2 [B][h*h][128] are ACCUMULATED into (atomics: sampled pixels repeat); the caller zeroes them
 int hcm_dense_affinity_bwd(const float* G1, const float* G2, const long long* pix, const float* stat, const float* kept,
-                           const float* fin, int B, int S, int h, int dim, float inv_T, float gscale, float* dG1, float* dG2,
-                           cudaStream_t stream) {
+                           const float* fin, int B, int S, int h, int dim, float inv_T, float gscale_r2d, float gscale_d2r, float* dG1,
+                           float* dG2, cudaStream_t stream) {
   HCM_CHECK_ARG(G1 && G2 && pix && stat && kept && fin && dG1 && dG2, "dense_affinity_bwd: null pointer");
   HCM_CHECK_ARG(dim == DA_C && B >= 1 && S >= 1 && h >= 1, "dense_affinity_bwd: bad args (dim=%d B=%d S=%d h=%d)", dim, B, S, h);
   DaParams p = {};
   p.G1 = G1; p.G2 = G2; p.pix = pix; p.kept = kept; p.fin = fin; p.stat = const_cast<float*>(stat);
-  p.dG1 = dG1; p.dG2 = dG2; p.inv_T = inv_T; p.gscale = gscale;
+  p.dG1 = dG1; p.dG2 = dG2; p.inv_T = inv_T; p.gscale = gscale_r2d; p.gscale_o = gscale_d2r;
   p.g = da_geo(S, h, true);
   HCM_CHECK_ARG(p.g.smem_bytes <= 227 * 1024, "dense_affinity_bwd: shared memory (%u bytes)", p.g.smem_bytes);
   static bool attr = false;

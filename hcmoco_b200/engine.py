@@ -67,14 +67,33 @@ class ParamStore:
         self.p = K.zeros(off)
         self.g = K.zeros(off)
         self.m = K.zeros(off)
-        self.buffers = OrderedDict()
+        # BatchNorm buffers: ONE flat fp32 tensor (running_mean / running_var) and ONE int64 tensor (num_batches_tracked) with
+        # per-key views — no per-key allocation / fill launches (619 BN layers), and save / restore is two copies
+        nf = sum(shp[0] for k, shp in keys.items() if k.endswith(("running_mean", "running_var")))
+        nt = sum(1 for k in keys if k.endswith("num_batches_tracked"))
+        init = torch.zeros(nf)
+        spans, o, t = [], 0, 0
         for k, shp in keys.items():
             if k.endswith("num_batches_tracked"):
-                self.buffers[k] = K.zeros((), dtype=torch.int64)
-            elif k.endswith("running_mean"):
-                self.buffers[k] = K.zeros(*shp)
-            elif k.endswith("running_var"):
-                self.buffers[k] = K.zeros(*shp) + 1.0
+                spans.append((k, None, t))
+                t += 1
+            elif k.endswith(("running_mean", "running_var")):
+                if k.endswith("running_var"):
+                    init[o:o + shp[0]] = 1.0
+                spans.append((k, o, shp[0]))
+                o += shp[0]
+        self.bflat = init.to(device=K.device, dtype=K.dtype)
+        self.nbt = torch.zeros(nt, dtype=torch.int64, device=K.device)
+        self.buffers = OrderedDict()
+        for k, o, n in spans:
+            self.buffers[k] = self.nbt[n] if o is None else self.bflat[o:o + n]
+
+    def save_buffers(self):
+        return self.bflat.clone(), self.nbt.clone()
+
+    def restore_buffers(self, saved):
+        self.bflat.copy_(saved[0])
+        self.nbt.copy_(saved[1])
 
     def view(self, flat, key):
         o, n = self.off[key]
@@ -259,6 +278,8 @@ class Engine:
         self.nnz = len(rows)
         self.n_data, self.K1, self.T_nce, self.m_nce = n_data, nce_k + 1, nce_t, nce_m
         self.T, self.S = temperature, num_samples
+        assert width in (18, 32), ("HRNet-w%d: the BatchNorm / pooling / tensor-core kernels tile at most 256 channels (w18: 144, "
+                                   "w32: 256); w48's 384-channel stage-4 branch is not built (no shipped pre-train script uses it)" % width)
         self.world = world_size
         self.two_streams = two_streams   # encoder2 on a side stream (see Plan)
         self.fuse_bn_finalize = fuse_bn_finalize     # see _bn_stats
@@ -843,6 +864,12 @@ class Engine:
         def backward():
             p.b(K.zero, self.df, self.df.numel() * self.df.element_size())
             p.b(bwd)
+            if not self.feat3_slot["ready"]:
+                # first stage: no objective writes d(loss)/d(feat3) before the joint mean does.  Its slot is zeroed HERE (the loss
+                # part of the program) and marked ready, so the model part accumulates into it: the autograd bridge, which skips the
+                # loss part and seeds the slot with the caller's gradient (`seed_output_grads`), then keeps that gradient
+                g, _ = self._slot_grad(self.feat3_slot, (B, self.J, 128))
+                p.b(K.zero, g, g.numel() * g.element_size())
 
         p.on_backward(backward)
 
@@ -910,7 +937,7 @@ class Engine:
             gs, acc = self._slot_grad(self.feat3_slot, (B, J, 128))
             p.b(K.gather_l2norm_bwd, dSk, 128, Sk, 128, inv_s, None, 0, 1, B * J, 128, gs, 128, acc)
             # dense: affinity recomputed on chip, logit gradient -> second MMA -> L2-norm backward -> atomic scatter
-            p.b(K.dense_affinity_bwd, G1.data, G2.data, self.dense_idx, stat, kept, fin_d, B, S, h, 128, iT, 1.0, g1, g2)
+            p.b(K.dense_affinity_bwd, G1.data, G2.data, self.dense_idx, stat, kept, fin_d, B, S, h, 128, iT, 1.0, 1.0, g1, g2)
 
         p.on_backward(backward)
 
@@ -999,18 +1026,16 @@ class Engine:
 
     # ---- CUDA graph: forward + losses + backward are one graph launch (every buffer is static)
     def capture(self):
-        saved = [(b, b.clone()) for b in self.store.buffers.values()]
+        saved = self.store.save_buffers()
         self.forward()                     # warm-up outside capture (module loading), then undo its BN side effects
         self.backward()
-        for b, c in saved:
-            b.copy_(c)
+        self.store.restore_buffers(saved)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.forward()
             self.backward()
-        for b, c in saved:
-            b.copy_(c)
+        self.store.restore_buffers(saved)
         return self
 
     def step_graph(self, lr=0.03, momentum=0.9, wd=1e-4):

@@ -35,7 +35,7 @@ class TrainOptions(object):
         a("--not_use_weighted_sampler", action="store_true", default=False); a("--temperature", type=float, default=0.07)
         a("--random_flip", type=int, default=0); a("--jigsaw", action="store_true")
         a("--mem", default="bank", type=str, choices=["bank", "bank+jointspri3d"]); a("--arch", default="HRNet", type=str)
-        a("-d", "--feat_dim", default=128, type=int); a("-k", "--nce_k", default=16384, type=int)
+        a("-d", "--feat_dim", default=128, type=int); a("-k", "--nce_k", default=65536, type=int)
         a("-m", "--nce_m", default=0.5, type=float); a("-t", "--nce_t", default=0.07, type=float)
         a("--alpha", default=0.999, type=float); a("--head", default="linear", type=str); a("--resume", default="", type=str)
         a("--world-size", default=-1, type=int); a("--rank", default=-1, type=int)

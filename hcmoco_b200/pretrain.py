@@ -56,32 +56,38 @@ def init_parameters(store, seed=0):
 
 
 class InputStager:
-    """Double-buffered host->device staging of the big per-step input (the [B,6,R,R] RGB-D tensor: 100 MB at B=64, ~2.3 ms
-    over PCIe) on a copy stream, so that the copy of step i+1 overlaps the kernels of step i; the step itself then starts
-    with a device-to-device copy into the static buffer the CUDA graph reads."""
+    """Double-buffered host->device staging of a step's inputs on a copy stream, so that the copies of step i+1 (the [B,6,R,R]
+    RGB-D tensor alone is 100 MB at B=64, ~2 ms over PCIe) overlap the kernels of step i; the step itself then starts with
+    device-to-device copies into the static buffers the CUDA graph reads.  `like` = one device tensor or a list of them."""
 
     def __init__(self, like):
-        self.buf = [torch.empty_like(like), torch.empty_like(like)]
-        self.free = [torch.cuda.Event(), torch.cuda.Event()]        # slot consumed (its D2D copy is enqueued)
+        self.single = not isinstance(like, (list, tuple))
+        like = [like] if self.single else list(like)
+        self.buf = [[torch.empty_like(t) for t in like] for _ in range(2)]
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]        # slot consumed (its D2D copies are enqueued)
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]       # H2D into the slot done
         self.stream = torch.cuda.Stream()
         self.slot = 0
         for ev in self.free:
             ev.record()
 
-    def stage(self, x_host):
+    def stage(self, host):
+        host = [host] if self.single else host
         k = self.slot
         self.slot ^= 1
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self.free[k])
-            self.buf[k].copy_(x_host, non_blocking=True)
+            for b, t in zip(self.buf[k], host):
+                b.copy_(t, non_blocking=True)
             self.ready[k].record(self.stream)
         return k
 
     def consume(self, k, dst):
+        dst = [dst] if self.single else dst
         cur = torch.cuda.current_stream()
         cur.wait_event(self.ready[k])
-        dst.copy_(self.buf[k], non_blocking=True)
+        for d, b in zip(dst, self.buf[k]):
+            d.copy_(b, non_blocking=True)
         self.free[k].record(cur)
 
 
@@ -124,32 +130,41 @@ class PretrainStep:
             w = torch.where(has, m, torch.ones_like(m))          # rows of dropped samples are ignored downstream
             e.dense_idx.copy_(torch.multinomial(w, e.S, replacement=True, generator=self.gen))
 
+    def _targets(self):
+        """(tuple position in the reference's batch layout, static device buffer) of every input the step reads: the depth mask
+        (16.8 MB at B=64) only feeds the dense objective, so the first stage never moves it."""
+        e = self.eng
+        t = [(0, e.x), (1, e.index), (2, e.skel), (4, e.joints_yx), (5, e.joints_vis), (6, e.use_depth)]
+        if e.stage == 2:
+            t.append((7, e.depth_mask))
+        return t
+
+    def h2d_bytes(self, batch):
+        return sum(batch[i].numel() * batch[i].element_size() for i, _ in self._targets())
+
     def prefetch(self, batch):
-        """Start the host->device copy of the NEXT step's RGB-D tensor on the copy stream while the current step computes;
+        """Start the host->device copies of the NEXT step's inputs on the copy stream while the current step computes;
         `run(batch)` recognises a prefetched batch by identity.  Only meaningful for pinned host batches."""
         x = batch[0]
         if x.is_cuda:
             return
+        tg = self._targets()
         if self.stager is None:
-            self.stager = InputStager(self.eng.x)
-        self._staged[id(x)] = (x, self.stager.stage(x))
+            self.stager = InputStager([d for _, d in tg])
+        self._staged[id(x)] = (x, self.stager.stage([batch[i] for i, _ in tg]))
 
     def run(self, batch, next_batch=None):
         e = self.eng
         data = batch
+        tg = self._targets()
         hit = self._staged.pop(id(data[0]), None)
         if hit is not None and hit[0] is data[0]:
-            self.stager.consume(hit[1], e.x)
+            self.stager.consume(hit[1], [d for _, d in tg])
         else:
-            e.x.copy_(data[0], non_blocking=True)
+            for i, d in tg:
+                d.copy_(data[i], non_blocking=True)
         if next_batch is not None:
             self.prefetch(next_batch)
-        e.index.copy_(data[1], non_blocking=True)
-        e.skel.copy_(data[2], non_blocking=True)
-        e.joints_yx.copy_(data[4], non_blocking=True)
-        e.joints_vis.copy_(data[5], non_blocking=True)
-        e.use_depth.copy_(data[6], non_blocking=True)
-        e.depth_mask.copy_(data[7], non_blocking=True)
         self.draw(batch)
         if self.use_graph:
             e.graph.replay()
@@ -178,7 +193,7 @@ class PretrainStep:
         """Device time of every C-ABI launch of one real step (CUDA events on the launching stream around
         each call, no graph), summed per entry point."""
         e = self.eng
-        saved = [(b, b.clone()) for b in e.store.buffers.values()]
+        saved = e.store.save_buffers()
         g_saved = e.store.g.clone()
         self.run(batch)                       # make inputs current
         torch.cuda.synchronize()
@@ -216,7 +231,6 @@ class PretrainStep:
                 dd = self.detail.setdefault(sh, {"ms": 0.0, "calls": 0})
                 dd["ms"] += t
                 dd["calls"] += 1
-        for b, c in saved:
-            b.copy_(c)
+        e.store.restore_buffers(saved)
         e.store.g.copy_(g_saved)
         return fam

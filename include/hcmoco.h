@@ -162,13 +162,14 @@ int hcm_dense_finish(const float* stat, const float* kept, const long long* use_
    L2-normalise (:692-693), S x S x 128 affinity on tcgen05 tensor cores (bf16 hi/lo split, fp32 accumulation in TMEM;
    :695-699), soft-target log-softmax statistics (:702-721) in the epilogue.  Nothing S x S is written to memory.
    stat [B][2][S][4] is scratch kept for the backward; fin[5] = loss_r2d, loss_d2r, acc_r2d, acc_d2r, B'.
-   The backward recomputes the affinity and ACCUMULATES into dG1, dG2 (atomics; the caller zeroes them). */
+   The backward recomputes the affinity and ACCUMULATES into dG1, dG2 (atomics; the caller zeroes them);
+   gscale_r2d / gscale_d2r = d(total)/d(loss_r2d), d(total)/d(loss_d2r) (1, 1 for the reference's plain sum, :980). */
 int hcm_dense_affinity_fwd(const float* G1, const float* G2, const long long* pix, const float* kept,
                            const long long* use_depth, int B, int S, int h, int dim, float inv_T, float* stat, float* fin,
                            cudaStream_t stream);
 int hcm_dense_affinity_bwd(const float* G1, const float* G2, const long long* pix, const float* stat, const float* kept,
-                           const float* fin, int B, int S, int h, int dim, float inv_T, float gscale, float* dG1, float* dG2,
-                           cudaStream_t stream);
+                           const float* fin, int B, int S, int h, int dim, float inv_T, float gscale_r2d, float gscale_d2r,
+                           float* dG1, float* dG2, cudaStream_t stream);
 int hcm_joint_stats(const float* Lr, const float* Ld, const int* joints_vis, const long long* use_depth, int B, int J,
                     float* rs, float* lse, float* fin, cudaStream_t stream);
 int hcm_joint_grad(float* Lr, float* Ld, const int* joints_vis, const long long* use_depth, const float* lse,

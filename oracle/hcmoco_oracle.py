@@ -277,10 +277,11 @@ def _sem_gconv(P, p, x, mask):
     h0 = x @ W[0]
     h1 = x @ W[1]
     J = mask.shape[0]
+    mask = mask.to(x.device)
     rows, cols = mask.nonzero(as_tuple=True)
-    A = torch.full((J, J), -9e15, dtype=x.dtype).index_put((rows, cols), e.reshape(-1))
+    A = torch.full((J, J), -9e15, dtype=x.dtype, device=x.device).index_put((rows, cols), e.reshape(-1))
     A = torch.softmax(A, dim=1)
-    eye = torch.eye(J, dtype=x.dtype)
+    eye = torch.eye(J, dtype=x.dtype, device=x.device)
     return (A * eye) @ h0 + (A * (1 - eye)) @ h1 + b.view(1, 1, -1)
 
 
@@ -366,27 +367,27 @@ def bank_update(bank, x, y, m=0.5):
 def _top1(logit):
     # learning/util.py:24-38 with target 0: fraction (in %) of rows whose arg-max is column 0
     if logit.shape[0] == 0:
-        return torch.tensor(float("nan"))
+        return torch.tensor(float("nan"), device=logit.device)
     return (logit.argmax(1) == 0).to(logit.dtype).mean() * 100.0
 
 
 def nce_losses(logits, use_depth=None, use_rgb=None):
     """ContrastTrainer._compute_loss_accuracy (contrast_trainer.py:212-253) with target 0."""
     def ce(l):
-        return F.cross_entropy(l, torch.zeros(l.shape[0], dtype=torch.long))
+        return F.cross_entropy(l, torch.zeros(l.shape[0], dtype=torch.long, device=l.device))
 
     if use_rgb is not None:
         sel = (use_depth == 1) & (use_rgb == 1)
         if sel.sum() == 0:
             losses = [(l - l).sum() for l in logits[:-2]] + [ce(l) for l in logits[-2:]]
-            accs = [torch.zeros(())] * 4 + [_top1(l) for l in logits[-2:]]
+            accs = [torch.zeros((), device=logits[0].device)] * 4 + [_top1(l) for l in logits[-2:]]
             return losses, accs
         return [ce(l[sel]) for l in logits], [_top1(l[sel]) for l in logits]
     if use_depth is not None:
         sel = use_depth == 1
         if use_depth.sum() == 0:
             losses = [(l - l).sum() for l in logits[:-2]] + [ce(l) for l in logits[-2:]]
-            accs = [torch.zeros(())] * 4 + [_top1(l) for l in logits[-2:]]
+            accs = [torch.zeros((), device=logits[0].device)] * 4 + [_top1(l) for l in logits[-2:]]
             return losses, accs
         losses = [ce(l[sel]) if i <= 3 else ce(l) for i, l in enumerate(logits)]
         accs = [_top1(l[sel]) if i <= 3 else _top1(l) for i, l in enumerate(logits)]
@@ -411,7 +412,7 @@ def dense_loss(G1, G2, depth_mask, sample_idx, use_depth=None, T=0.07):
     """
     if use_depth is not None and use_depth.sum() == 0:
         z = (G1 - G1 + G2 - G2).mean()
-        return [z, z], [torch.zeros(()), torch.zeros(())]
+        return [z, z], [torch.zeros((), device=z.device), torch.zeros((), device=z.device)]
     B, C, h, w = G1.shape
     _, keep = dense_kept_samples(depth_mask, h)
     idx = sample_idx[keep]
@@ -428,7 +429,7 @@ def dense_loss(G1, G2, depth_mask, sample_idx, use_depth=None, T=0.07):
     soft = torch.softmax(-dist, 1)
     losses = [-(soft * F.log_softmax(L, 1)).sum(-2).mean(),
               -(soft * F.log_softmax(Lt, 1)).sum(-2).mean()]
-    tgt = torch.arange(S).unsqueeze(0)
+    tgt = torch.arange(S, device=L.device).unsqueeze(0)
     accs = [((L.argmax(-2) == tgt).sum(-1).to(L.dtype) / S).mean(),
             ((Lt.argmax(-2) == tgt).sum(-1).to(L.dtype) / S).mean()]
     return losses, accs
@@ -450,7 +451,7 @@ def joint_loss(G1, G2, feat3, joints_yx, joints_vis, use_depth=None, T=0.07):
     s = F.normalize(feat3, dim=-1)                                        # [B,J,C]
     Lr = torch.matmul(s, a) / T                                           # [B,J(skel),J(pixel)]
     Ld = torch.matmul(s, d) / T
-    tgt = torch.arange(J).unsqueeze(0).repeat(B, 1)
+    tgt = torch.arange(J, device=Lr.device).unsqueeze(0).repeat(B, 1)
     tgt[joints_vis == 0] = -100
     dtgt = tgt.clone()
     if use_depth is not None:
@@ -472,16 +473,16 @@ def scl_loss(G1, G2, joints_yx, use_depth, use_rgb=None, T=0.07):
     B, C, h, w = G1.shape
     J = joints_yx.shape[1]
     if use_rgb is None:
-        use_rgb = torch.ones(B, dtype=torch.long)
+        use_rgb = torch.ones(B, dtype=torch.long, device=G1.device)
     if use_depth is None:
-        use_depth = torch.ones(B, dtype=torch.long)
+        use_depth = torch.ones(B, dtype=torch.long, device=G1.device)
     p = joint_pixel_index(joints_yx, h).unsqueeze(1).expand(-1, C, -1)
     a = F.normalize(torch.gather(G1.reshape(B, C, h * w), 2, p), dim=1).permute(0, 2, 1).reshape(B * J, C)
     d = F.normalize(torch.gather(G2.reshape(B, C, h * w), 2, p), dim=1).permute(0, 2, 1).reshape(B * J, C)
     Fm = torch.cat([a, d], 0)
     N = 2 * B * J
     logp = F.log_softmax(Fm @ Fm.t() / T, 1)
-    r = torch.arange(N)
+    r = torch.arange(N, device=G1.device)
     pos = ((r.view(-1, 1) % J) == (r.view(1, -1) % J)) & (r.view(-1, 1) != r.view(1, -1))
     off = torch.cat([(use_rgb == 0).view(B, 1).expand(B, J).reshape(-1),
                      (use_depth == 0).view(B, 1).expand(B, J).reshape(-1)])

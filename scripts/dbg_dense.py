@@ -41,9 +41,9 @@ for (B, h, S) in ((4, 16, 60), (3, 32, 400), (32, 64, 400), (2, 8, 130)):
         out["ref"][1][:2].tolist()), flush=True)
     stat, fin = out["ref"]
     d1r, d2r = torch.zeros_like(G1), torch.zeros_like(G2)
-    R.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1.0 / T, 1.0, d1r, d2r)
+    R.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1.0 / T, 1.0, 1.0, d1r, d2r)
     d1, d2 = torch.zeros_like(G1), torch.zeros_like(G2)
-    K.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1.0 / T, 1.0, d1, d2)
+    K.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1.0 / T, 1.0, 1.0, d1, d2)
     torch.cuda.synchronize()
     print("   bwd: dG1 %.2e dG2 %.2e" % (rel(d1, d1r), rel(d2, d2r)), flush=True)
     if B == 32:
@@ -56,7 +56,7 @@ for (B, h, S) in ((4, 16, 60), (3, 32, 400), (32, 64, 400), (2, 8, 130)):
                 K.dense_affinity_fwd(G1, G2, pix, kept, use_depth, B, S, h, 128, 1.0 / T, stat, fin)
             ev[1].record()
             for i in range(20):
-                K.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1.0 / T, 1.0, d1, d2)
+                K.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1.0 / T, 1.0, 1.0, d1, d2)
             ev[2].record()
             torch.cuda.synchronize()
         nk = int(kept.sum())

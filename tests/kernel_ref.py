@@ -491,7 +491,7 @@ class TorchKernels:
         sv[k != 0] = st[k != 0]          # the fused kernel skips dropped samples
         return 0
 
-    def dense_affinity_bwd(self, G1, G2, pix, stat, kept, fin, B, S, h, dim, inv_T, gscale, dG1, dG2):
+    def dense_affinity_bwd(self, G1, G2, pix, stat, kept, fin, B, S, h, dim, inv_T, gscale_r2d, gscale_d2r, dG1, dG2):
         HW = h * h
         mk = lambda *s: torch.empty(*s, dtype=G1.dtype, device=G1.device)      # noqa: E731
         A, D, ia, idn = mk(B * S, dim), mk(B * S, dim), mk(B * S), mk(B * S)
@@ -501,7 +501,14 @@ class TorchKernels:
         L = torch.matmul(D3, A3.transpose(1, 2)) * inv_T
         k = kept.reshape(-1)[:B]
         st = torch.where(k.view(B, 1, 1, 1) != 0, stat.reshape(B, 2, S, 4), torch.ones_like(stat.reshape(B, 2, S, 4)))
-        self.dense_grad(L, pix, st, kept, fin, B, S, h, gscale)
+        # dense_grad with one weight per direction: loss_r2d owns the column statistics (st[:,0]), loss_d2r the row ones
+        w = self._dense_w(pix, B, S, h, L.dtype)
+        nk = float(fin[4])
+        c0, c1 = (gscale_r2d / (nk * S), gscale_d2r / (nk * S)) if nk > 0 else (0.0, 0.0)
+        col_lse, col_Z = st[:, 0, :, 0].unsqueeze(1), st[:, 0, :, 1].unsqueeze(1)
+        row_lse, row_Z = st[:, 1, :, 0].unsqueeze(2), st[:, 1, :, 1].unsqueeze(2)
+        g = c0 * (torch.exp(L - col_lse) - w / col_Z) + c1 * (torch.exp(L - row_lse) - w / row_Z)
+        L = g * (k != 0).to(L.dtype).view(B, 1, 1)
         dD = (torch.matmul(L, A3) * inv_T).reshape(B * S, dim)
         dA = (torch.matmul(L.transpose(1, 2), D3) * inv_T).reshape(B * S, dim)
         self.gather_l2norm_bwd(dA.contiguous(), dim, A, dim, ia, pix, HW, S, B * S, dim, dG1, 0, 1)

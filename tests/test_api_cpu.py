@@ -218,3 +218,114 @@ def test_loss_methods_match_oracle():
     l, _ = tr._compute_cross_subject_joints_pri3d_loss(G1, G2, None, None, batch["joints_yx"], batch["joints_vis"],
                                                        use_depth=batch["use_depth"], K=K)
     assert rel(l[0], O.scl_loss(G1, G2, batch["joints_yx"], batch["use_depth"])) < 1e-9
+
+
+def test_loss_methods_backpropagate_like_the_reference():
+    """`sum(losses).backward()` through the three reference-signature loss methods (contrast_trainer.py:642, 744, 830):
+    gradients wrt both projection maps and the skeleton features equal the oracle's autograd gradients, also with
+    unequal weights on the loss terms."""
+    dt = torch.float64
+    K = K64()
+    B, J, h, S = 3, 13, 16, 40
+    g = torch.Generator().manual_seed(1)
+    base = [torch.randn(B, 128, h, h, generator=g, dtype=dt), torch.randn(B, 128, h, h, generator=g, dtype=dt),
+            torch.randn(B, J, 128, generator=g, dtype=dt)]
+    batch, _, _ = make_inputs(dict(CFG, B=B), 0, dt)
+    dense = torch.randint(0, h * h, (B, S), generator=g)
+    tr = api.ContrastTrainer(make_opt(dict(CFG, S=S)))
+    wts = [1.0, 0.25, 2.0, 1.0, 0.5]
+
+    def total(fn_dense, fn_joint, fn_scl, G1, G2, f3):
+        dl = fn_dense(G1, G2)
+        jl = fn_joint(G1, G2, f3)
+        sl = fn_scl(G1, G2)
+        return wts[0] * dl[0] + wts[1] * dl[1] + wts[2] * jl[0] + wts[3] * jl[1] + wts[4] * sl
+
+    def run(engine):
+        G1, G2, f3 = [t.clone().requires_grad_(True) for t in base]
+        if engine:
+            t = total(lambda a, b: tr._compute_soft_pri3d_loss_accuracy(a, b, None, None, use_depth=batch["use_depth"],
+                                                                        depth_mask=batch["depth_mask"], sample_idx=dense, K=K)[0],
+                      lambda a, b, c: tr._compute_joints_pri3d_loss_accuracy(a, b, c, None, batch["joints_yx"], batch["joints_vis"],
+                                                                             use_depth=batch["use_depth"], K=K)[0],
+                      lambda a, b: tr._compute_cross_subject_joints_pri3d_loss(a, b, None, None, batch["joints_yx"],
+                                                                               batch["joints_vis"], use_depth=batch["use_depth"],
+                                                                               K=K)[0][0], G1, G2, f3)
+        else:
+            t = total(lambda a, b: O.dense_loss(a, b, batch["depth_mask"], dense, batch["use_depth"])[0],
+                      lambda a, b, c: O.joint_loss(a, b, c, batch["joints_yx"], batch["joints_vis"], batch["use_depth"])[0],
+                      lambda a, b: O.scl_loss(a, b, batch["joints_yx"], batch["use_depth"]), G1, G2, f3)
+        t.backward()
+        return float(t), G1.grad, G2.grad, f3.grad
+
+    e, r = run(True), run(False)
+    assert abs(e[0] - r[0]) < 1e-9 * abs(r[0])
+    for a, b, name in zip(e[1:], r[1:], ("d/dG1", "d/dG2", "d/dfeat3")):
+        assert float(b.abs().sum()) > 0 and rel(a, b) < 1e-8, (name, rel(a, b))
+
+
+def test_drop_in_loop_zero_grad_backward_step_twice():
+    """The documented drop-in loop — optimizer.zero_grad(); loss.backward(); optimizer.step() with the FusedSGD that
+    wrap_up returns, and with plain torch.optim.SGD(set_to_none=False) — against the oracle over TWO iterations: a
+    gradient buffer aliased between autograd and the engine would double the gradient from the second one on."""
+    dt = torch.float64
+    cfg = dict(CFG, stage=1)
+    for mode in ("fused", "fused_keep", "torch_keep"):
+        K = K64()
+        layout, P, mom, banks = oracle_state(cfg, dt)
+        opt = make_opt(cfg)
+        model, _ = api.build_model(opt, kernels=K)
+        model.store.load_state_dict(P)
+        mem = api.build_mem(opt, cfg["n"], kernels=K)
+        for i in range(3):
+            getattr(mem, "memory_%d" % (i + 1)).copy_(banks[i])
+        tr = api.build_contrast(opt)
+        sgd = torch.optim.SGD(model.parameters(), lr=0.03, momentum=0.9, weight_decay=1e-4)
+        optimizer = sgd if mode == "torch_keep" else tr.wrap_up(model, None, sgd)[2]
+        crit = torch.nn.CrossEntropyLoss()
+        for s in range(2):
+            batch, nce, dense = make_inputs(cfg, s, dt)
+            ref = O.train_step(P, mom, banks, batch, nce, dense, width=cfg["width"], skeleton=cfg["skeleton"], stage=1,
+                               first=(s == 0))
+            mem.injected_idx = nce.clone()
+            f = model(batch["x"], batch["skeleton"])
+            f1, f2, f3 = torch.chunk(f, 3, dim=1)
+            out = mem(f1, f2, f3, batch["index"])
+            sel = batch["use_depth"] == 1
+            loss = sum(crit(l[sel] if i <= 3 else l, out[-1][sel] if i <= 3 else out[-1]) for i, l in enumerate(out[:-1]))
+            if mode == "fused":
+                optimizer.zero_grad()
+            else:
+                optimizer.zero_grad(set_to_none=False)
+            loss.backward()
+            g = model.encoder1.conv1.weight.grad
+            assert rel(g, ref["grads"]["encoder1.conv1.weight"]) < 1e-7, (mode, s, rel(g, ref["grads"]["encoder1.conv1.weight"]))
+            optimizer.step()
+            assert rel(loss.detach(), ref["loss"]) < 1e-9, (mode, s)
+        sd = model.store.state_dict()
+        for k in ("encoder1.conv1.weight", "encoder2.stage4.2.fuse_layers.3.0.2.0.weight", "head3.0.weight"):
+            assert rel(sd[k], P[k]) < 1e-8, (mode, k, rel(sd[k], P[k]))
+
+
+def test_stage1_feat3_gradient_reaches_the_skeleton_encoder():
+    """return_fm=True in the first stage: feat3 / avg_feat3 are differentiable outputs (build_backbone.py:296-303); their
+    gradient must reach encoder3 (the joint-mean backward accumulates into the seeded slot instead of overwriting it)."""
+    dt = torch.float64
+    cfg = dict(CFG, stage=1)
+    K = K64()
+    layout, P, mom, banks = oracle_state(cfg, dt)
+    model, _ = api.build_model(make_opt(cfg), kernels=K)
+    model.store.load_state_dict(P)
+    batch, _, _ = make_inputs(cfg, 0, dt)
+    outs = model(batch["x"], batch["skeleton"], return_fm=True)
+    feat3, f = outs[2], outs[-1]
+    (feat3.square().sum() + f[:, 256:].sum()).backward()
+    got = model.encoder3.gconv_output.W.grad.clone()
+    for k, v in P.items():
+        if O.is_param(k):
+            v.requires_grad_(True)
+            v.grad = None
+    o = O.model_forward(P, batch["x"], batch["skeleton"], cfg["width"], cfg["skeleton"], 1, True)
+    (o["feat3"].square().sum() + o["f"][:, 256:].sum()).backward()
+    want = P["encoder3.gconv_output.W"].grad
+    assert float(want.abs().sum()) > 0 and rel(got, want) < 1e-8, rel(got, want)

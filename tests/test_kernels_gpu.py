@@ -275,8 +275,8 @@ def test_gather_l2norm(KK):
          [10], tol=1e-4)
 
 
-@pytest.mark.parametrize("B,h,S", [(4, 16, 60), (3, 32, 400), (2, 8, 130), (5, 64, 400)])
-def test_dense_affinity_fused(KK, B, h, S):
+@pytest.mark.parametrize("B,h,S,gs", [(4, 16, 60, (1.0, 1.0)), (3, 32, 400, (1.0, 1.0)), (2, 8, 130, (0.3, 2.0)), (5, 64, 400, (1.0, 0.0))])
+def test_dense_affinity_fused(KK, B, h, S, gs):
     """Fused tcgen05 dense-affinity kernels (gather + L2-norm + S x S x 128 affinity + soft-target statistics; backward by
     recompute + second MMA + atomic scatter) against the unfused fp32 statement (contrast_trainer.py:684-723)."""
     kc, kr = KK
@@ -303,7 +303,7 @@ def test_dense_affinity_fused(KK, B, h, S):
     d = []
     for kk in (kc, kr):
         d1, d2 = torch.zeros_like(G1), torch.zeros_like(G2)
-        kk.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, iT, 1.0, d1, d2)
+        kk.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, iT, gs[0], gs[1], d1, d2)
         d.append((d1, d2))
     torch.cuda.synchronize()
     assert rel(d[0][0], d[1][0]) < 2e-4 and rel(d[0][1], d[1][1]) < 2e-4
@@ -312,7 +312,7 @@ def test_dense_affinity_fused(KK, B, h, S):
     kc.dense_affinity_fwd(G1, G2, pix, kept, torch.zeros_like(use_depth), B, S, h, 128, iT, stat, fin)
     assert float(fin[:5].abs().sum()) == 0.0
     d1, d2 = torch.zeros_like(G1), torch.zeros_like(G2)
-    kc.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, iT, 1.0, d1, d2)
+    kc.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, iT, gs[0], gs[1], d1, d2)
     assert float(d1.abs().sum() + d2.abs().sum()) == 0.0
 
 
