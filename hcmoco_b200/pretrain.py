@@ -103,6 +103,7 @@ class PretrainStep:
         self.eng.init_banks(seed=seed)               # identical on every rank (all three banks)
         self.eng.build()
         self.stager, self._staged = None, {}
+        self.injected = None
         self.gen = torch.Generator(device="cuda").manual_seed(1000 + rank)
         self.use_graph = use_graph
         if use_graph:
@@ -120,6 +121,11 @@ class PretrainStep:
         """Negative indices (memory/alias_multinomial.py:49-65 with uniform probabilities = uniform draw,
         idx[:,0] = own row, mem_bank.py:176-177) and the dense pixel samples (contrast_trainer.py:674-685)."""
         e = self.eng
+        if self.injected is not None:           # tests: (nce_idx [B,K+1], dense_idx [B,S] or None)
+            e.nce_idx.copy_(self.injected[0])
+            if e.stage == 2:
+                e.dense_idx.copy_(self.injected[1])
+            return
         idx = torch.randint(0, e.n_data, (e.B, e.K1), device="cuda", generator=self.gen)
         idx[:, 0] = e.index
         e.nce_idx.copy_(idx)

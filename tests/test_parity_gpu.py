@@ -170,3 +170,244 @@ def test_reference_surface_on_gpu(K, tmp_path):
     model2, _ = api.build_model(make_opt(cfg))
     model2.store.load_state_dict(ck["model"])
     assert torch.equal(model2.store.p, model.store.p)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Parity at the BASELINE.json shapes themselves (the shapes bench.py and the multi-stream schedule actually run: other tile
+# counts, grid clamps, resident-vs-ring weight paths and split ranges than the small cases above).  C2 = configs[1], C3..C5 =
+# the per-GPU shards of configs[2..4] (global 256 / 256 / 128 over 8 GPUs).  One step from the oracle's state against the fp32
+# CPU oracle: embeddings, maps, every loss <= 1e-3; the gradient is compared with the fp32 oracle DIRECTLY (at B >= 16 the
+# batch statistics are well conditioned: no fp64 detour); then the CUDA SGD kernel and bank update against the oracle's.
+BASELINE_CASES = {
+    "C2_stage1_w18_b64_r256": dict(stage=1, width=18, skeleton="mpii", B=64, R=256, K=16384, n=165894, S=400),
+    "C3_stage2_w18_b32_r256_mpii": dict(stage=2, width=18, skeleton="mpii", B=32, R=256, K=16384, n=165894, S=400),
+    "C4_stage2_w18_b32_r256_coco": dict(stage=2, width=18, skeleton="coco_reduce", B=32, R=256, K=16384, n=165894, S=400),
+    "C5_stage2_w32_b16_r384": dict(stage=2, width=32, skeleton="mpii", B=16, R=384, K=16384, n=165894, S=400),
+}
+GRAD_FACTOR, GRAD_FLOOR = 4.0, 2e-2      # bar = max(FACTOR x [fp32 eager-GPU vs fp32 CPU distance], FLOOR); DESIGN.md section 6
+
+
+def _grad_cosine(g, ref):
+    dot = na = nb = 0.0
+    for k, v in ref.items():
+        a, b = g[k].detach().cpu().double().reshape(-1), v.detach().cpu().double().reshape(-1)
+        dot += float(a @ b)
+        na += float(a @ a)
+        nb += float(b @ b)
+    return dot / max((na * nb) ** 0.5, 1e-300)
+
+
+def _eager_gpu_vs_cpu(cfg, batch, nce, dense, grads_cpu):
+    from oracle import hcmoco_oracle as O
+    from engine_check import global_grad_err
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        layout, P, mom, banks = oracle_state(cfg, torch.float32)
+        P = type(P)((k, v.cuda()) for k, v in P.items())
+        out = O.train_step(P, {k: v.cuda() for k, v in mom.items()}, [b.cuda() for b in banks],
+                           {k: v.cuda() for k, v in batch.items()}, nce.cuda(), dense.cuda(), width=cfg["width"],
+                           skeleton=cfg["skeleton"], stage=cfg["stage"], first=True, apply_update=False)
+        g = {k: v.cpu() for k, v in out["grads"].items()}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+    del out, P
+    torch.cuda.empty_cache()
+    return global_grad_err(g, grads_cpu)[0], _grad_cosine(g, grads_cpu)
+
+
+@pytest.mark.parametrize("name", list(BASELINE_CASES))
+def test_baseline_shape_step_matches_fp32_oracle(K, name):
+    import gc
+    import json
+    from oracle import hcmoco_oracle as O
+    from engine_check import compare_forward, global_grad_err
+    from hcmoco_b200.engine import Engine
+    cfg = BASELINE_CASES[name]
+    torch.set_num_threads(os.cpu_count())
+    import psutil
+    need = (1.2 if cfg["width"] == 32 else 0.4) * cfg["B"] * (cfg["R"] / 256.0) ** 2 * (2 ** 30) + (6 << 30)   # oracle autograd (measured)
+    if psutil.virtual_memory().available < need:
+        pytest.skip("host memory: the CPU oracle needs ~%.0f GB at this shape" % (need / 2 ** 30))
+    layout, P, mom, banks = oracle_state(cfg, torch.float32)
+    eng = Engine(K, cfg["width"], cfg["stage"], cfg["skeleton"], cfg["B"], cfg["R"], cfg["n"], cfg["K"], num_samples=cfg["S"])
+    eng.store.load_state_dict(P)
+    eng.init_banks(banks)
+    eng.build()
+    batch, nce, dense = make_inputs(cfg, 0)
+    eng.set_batch(batch, nce, dense)
+    eng.forward()
+    eng.backward()
+    torch.cuda.synchronize()
+    res = eng.results()
+    g = eng.store.grads_dict()
+    ref = O.train_step(P, mom, banks, batch, nce, dense, width=cfg["width"], skeleton=cfg["skeleton"], stage=cfg["stage"],
+                       first=True)
+    errs = compare_forward(eng, res, ref, cfg, 1e-3, True, name)
+    ge, worst = global_grad_err(g, ref["grads"])
+    cos = _grad_cosine(g, ref["grads"])
+    print("   %s grads vs fp32 CPU oracle: global %.3e cos %.6f worst %s %.3e" % (name, ge, cos, worst[0], worst[1]), flush=True)
+    # calibration: how far apart are two fp32 implementations of the SAME math?  The oracle statement under PyTorch eager on the
+    # GPU (cuDNN / cuBLAS, TF32 disabled) against itself on the CPU (oneDNN): only summation order and algorithm choice differ.
+    own, own_cos = _eager_gpu_vs_cpu(cfg, batch, nce, dense, ref["grads"])
+    print("   %s fp32 eager-GPU oracle vs fp32 CPU oracle: global %.3e cos %.6f" % (name, own, own_cos), flush=True)
+    if os.environ.get("HCM_PARITY_SIMT"):        # diagnostic: the exact-fp32 SIMT convolution mode on the same inputs
+        del eng
+        gc.collect()
+        torch.cuda.empty_cache()
+        P0 = oracle_state(cfg, torch.float32)[1]
+        e2 = Engine(K, cfg["width"], cfg["stage"], cfg["skeleton"], cfg["B"], cfg["R"], cfg["n"], cfg["K"], num_samples=cfg["S"],
+                    use_tc=False)
+        e2.store.load_state_dict(P0)
+        e2.init_banks(oracle_state(cfg, torch.float32)[3])
+        e2.build()
+        e2.set_batch(batch, nce, dense)
+        e2.forward()
+        e2.backward()
+        torch.cuda.synchronize()
+        g2 = {k: v.cpu() for k, v in e2.store.grads_dict().items()}
+        ge2, w2 = global_grad_err(g2, ref["grads"])
+        print("   %s SIMT-fp32 engine vs fp32 CPU oracle: global %.3e cos %.6f; tensor-core vs SIMT engine: %.3e" % (
+            name, ge2, _grad_cosine(g2, ref["grads"]), global_grad_err(g, g2)[0]), flush=True)
+        eng = e2
+    assert ge < max(GRAD_FACTOR * own, GRAD_FLOOR), (ge, own, worst)
+    # the CUDA optimiser / bank kernels against the oracle's update: same gradient in, parameters + momentum out
+    for k, v in ref["grads"].items():
+        eng.store.load(eng.store.g, k, v)
+    eng.update_banks()
+    eng.sgd()
+    torch.cuda.synchronize()
+    pw = mw = 0.0
+    for k in mom:
+        pw = max(pw, rel(eng.store.export(eng.store.p, k), P[k]))
+        mw = max(mw, rel(eng.store.export(eng.store.m, k), mom[k]))
+    bw = max(rel(eng.banks[m], banks[m]) for m in range(3))
+    print("   %s after SGD: params %.2e momentum %.2e banks %.2e" % (name, pw, mw, bw), flush=True)
+    assert pw < 1e-5 and mw < 1e-5 and bw < 1e-5, (pw, mw, bw)
+    out = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_%s.json" % name), "w") as f:
+            json.dump({"forward": errs, "grad_global": ge, "grad_worst": list(worst), "params": pw, "momentum": mw, "banks": bw}, f)
+    del eng, ref, g
+    eng = None
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Two ranks through the CUDA path: per-rank loss = oracle on that rank's shard, the all-reduced gradient = the
+# mean of the per-rank oracle gradients, parameters / banks bit-identical across ranks after every step and equal to the
+# oracle's.  A one-GPU box cannot host two NCCL ranks, so both ranks share cuda:0 and the collectives run over gloo — the same
+# torch.distributed calls of PretrainStep.run (NCCL at N > 1 is covered by bench.py's `replicas_identical`).
+TWO_RANK_CFG = dict(stage=2, width=18, skeleton="mpii", B=4, R=64, K=256, n=1000, S=100)
+
+
+def _two_rank_worker(rank, world, port, q):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), here, os.path.join(here, "golden")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from oracle import hcmoco_oracle as O
+    from engine_check import global_grad_err
+    from hcmoco_b200.kernels import CudaKernels
+    from hcmoco_b200.pretrain import PretrainStep
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        cfg = TWO_RANK_CFG
+        K = CudaKernels()
+        step = PretrainStep(K, cfg["width"], cfg["stage"], cfg["skeleton"], cfg["B"], cfg["R"], cfg["n"], cfg["K"],
+                            num_samples=cfg["S"], world_size=world, rank=rank, use_graph=(rank == 0))   # one rank replays a graph
+        layout, P, mom, banks = oracle_state(cfg, torch.float32)
+        step.eng.store.load_state_dict(P)
+        for m in range(3):                                # in place: rank 0's captured graph holds the bank pointers
+            step.eng.banks[m].copy_(banks[m])
+        rep = []
+        for s in range(2):
+            shards = [make_inputs(cfg, 10 * r + s) for r in range(world)]
+            b, nce, dense = shards[rank]
+            step.injected = (nce.cuda(), dense.cuda())
+            data = [b["x"], b["index"], b["skeleton"], None, b["joints_yx"], b["joints_vis"], b["use_depth"], b["depth_mask"], None]
+            e = step.eng
+            snap = (e.store.p.clone(), e.store.m.clone(), [bk.clone() for bk in e.banks], e.store.save_buffers())
+            step.run([None if t is None else t.cuda() for t in data])
+            torch.cuda.synchronize()
+            res = step.results()
+            g_sum = e.store.g.clone()
+            after = (e.store.p.clone(), [bk.clone() for bk in e.banks], e.store.m.clone())
+            # (1) the collective wiring, exactly: the all-reduced gradient = the sum of the ranks' LOCAL gradients (recomputed from
+            # the pre-step state by the plain forward / backward programs, no collective) up to the fp32 atomics' summation order
+            e.store.p.copy_(snap[0]); e.store.m.copy_(snap[1]); e.store.restore_buffers(snap[3])
+            for m in range(3):
+                e.banks[m].copy_(snap[2][m])
+            e.forward()
+            e.backward()
+            g_loc = e.store.g.clone()
+            dist.all_reduce(g_loc)
+            wiring = rel(g_sum, g_loc)
+            # (2) against the oracle: every rank's step on its shard from the common state; mean gradient; rank-ordered gather
+            outs = []
+            for r in range(world):
+                br, nr, dr = shards[r]
+                Pr = type(P)((k, v.clone()) for k, v in P.items())
+                outs.append(O.train_step(Pr, O.make_momentum(Pr), [bk.clone() for bk in banks], br, nr, dr, width=cfg["width"],
+                                         skeleton=cfg["skeleton"], stage=cfg["stage"], first=True, apply_update=False))
+            gmean = {k: sum(o["grads"][k] for o in outs) / world for k in outs[0]["grads"]}
+            e.store.g.copy_(g_sum)
+            g = {k: v / world for k, v in e.store.grads_dict().items()}
+            ge, worst = global_grad_err(g, gmean)
+            all_f = torch.cat([o["f"] for o in outs])
+            all_y = torch.cat([sh[0]["index"] for sh in shards])
+            for m in range(3):
+                O.bank_update(banks[m], all_f[:, 128 * m:128 * (m + 1)], all_y, 0.5)
+            before = {k: P[k].clone() for k in mom}
+            O.sgd_step(P, gmean, mom, first=(s == 0))
+            # parameter update against the oracle's, relative to the size of the update (lr * gradient: carries the gradient's error)
+            num = den = 0.0
+            for k in mom:
+                pa = after[0][e.store.off[k][0]:e.store.off[k][0] + e.store.off[k][1]].cpu().double().reshape(-1)
+                num += float((pa - P[k].double().reshape(-1)).pow(2).sum())
+                den += float((before[k].double() - P[k].double()).pow(2).sum())
+            sums = torch.stack([t.view(torch.int32).to(torch.int64).sum() for t in (after[0], after[2], after[1][0], after[1][1], after[1][2])]).cpu()
+            allv = [torch.zeros_like(sums) for _ in range(world)]
+            dist.all_gather(allv, sums)
+            rep.append(dict(loss=rel(res["loss"], outs[rank]["loss"]), grad=ge, worst=worst, wiring=wiring,
+                            identical=bool(all(torch.equal(v, allv[0]) for v in allv)),
+                            banks=max(rel(after[1][m], banks[m]) for m in range(3)), update=(num / den) ** 0.5))
+            # resync the engine with the oracle (single-step parity per step)
+            step.eng.store.load_state_dict(P, strict=False)
+            for k in mom:
+                step.eng.store.load(step.eng.store.m, k, mom[k])
+            for m in range(3):
+                step.eng.banks[m].copy_(banks[m])
+        q.put((rank, rep))
+    except Exception as ex:      # surface the failure in the parent
+        import traceback
+        q.put((rank, "ERROR " + traceback.format_exc()[-2000:]))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def test_two_ranks_cuda_path_matches_oracle():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_two_rank_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=900) for _ in procs)
+    for p in procs:
+        p.join(60)
+    for r in range(2):
+        assert not isinstance(got[r], str), got[r]
+        for s, rep in enumerate(got[r]):
+            print("rank %d step %d: %s" % (r, s, rep), flush=True)
+            assert rep["identical"], (r, s)
+            assert rep["loss"] < 1e-3 and rep["banks"] < 1e-4 and rep["wiring"] < 1e-4, (r, s, rep)
+            assert rep["grad"] < 1e-1 and rep["update"] < 1e-1, (r, s, rep)   # B=4: the fp32 gradient itself is conditioned to ~1e-2
