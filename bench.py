@@ -376,10 +376,31 @@ def run_engine(a):
         for i in range(a.warmup):
             step.run(run.dev[i % 2])
         torch.cuda.synchronize()
+        log = os.environ.get("HCM_LAUNCH_LOG")      # conv launches of the profiled step in host order (zip with the ncu list)
+        if log:
+            names = []
+            for nm in ("tc_conv", "tc_wgrad", "tc_dgrad_s2", "conv2d_fwd", "conv2d_wgrad", "conv2d_dgrad"):
+                fn = getattr(K, nm)
+                o = {"tc_conv": 4, "conv2d_fwd": 4, "conv2d_dgrad": 3, "conv2d_wgrad": 3, "tc_wgrad": 4, "tc_dgrad_s2": 3}[nm]
+
+                def wrap(*args, _fn=fn, _nm=nm, _o=o):
+                    nl = 4 // K.tc_dgrad_s2_nqs(*args[3:8]) if _nm == "tc_dgrad_s2" else 1
+                    names.append("%s %dx%d %d->%d k%d%s|%d" % (_nm, args[_o + 1], args[_o + 2], args[_o + 3], args[_o + 4], args[_o + 5],
+                                                               "" if _nm == "tc_dgrad_s2" else " s%d" % args[_o + 6], nl))
+                    return _fn(*args)
+                setattr(K, nm, wrap)
+            step = run.step = type(step)(K, width=a.width, stage=a.stage, skeleton=a.skeleton, B=a.batch, R=a.res, n_data=a.n_data,
+                                         nce_k=a.nce_k, world_size=world, rank=rank, use_graph=False, seed=0)
+            step.run(run.dev[0])
+            torch.cuda.synchronize()
+            names.clear()
         torch.cuda.profiler.start()
         step.run(run.dev[0])
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+        if log:
+            with open(log, "w") as f:
+                f.write("\n".join(names) + "\n")
         return
     clocks = Clocks(local)
     if rank == 0:

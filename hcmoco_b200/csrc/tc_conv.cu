@@ -30,7 +30,7 @@ constexpr int NTHREADS = NTRANS + 128 + 64;  // then 4 epilogue warps, the TMA p
 constexpr int W_EPI = NTRANS / 32, W_TMA = W_EPI + 4, W_MMA = W_TMA + 1;
 constexpr int MAXG = 16;
 constexpr int MAX_LPAD = 512;
-constexpr int HDR_BYTES = 4096 + 6144;      // barriers / tmem ptr / scale / shift | row-concat boundary exchange (2 x 3 warps x 3 rows x 80 floats); the per-stage source tables follow
+constexpr int HDR_BYTES = 4096 + 6144 + 2048;   // barriers / tmem ptr / scale / shift | row-concat boundary exchange (2 x 3 warps x 3 rows x 80 floats) | issue schedule (descriptor low words); the per-stage source tables follow
 constexpr int MAX_ASTAGE = 4;
 constexpr int MAX_UNITS = 256;
 constexpr int MAX_STEPS = 144;                // 9 taps x 256/16 channels
@@ -44,7 +44,8 @@ struct Geo {
   int rc;            // row-concatenated taps (3x3 stride 1, 3*Npad <= 256): see make_geo
   int NB;            // N of one weight operand: 3*Npad (rc) or Npad
   int TM;            // output positions per tile: 126 (rc) or 128
-  long Mv, tiles;
+  int ksplit;        // 1, or 2: the filter taps of a tile are split over two CTAs (work unit = (tile, part)); see make_geo
+  long Mv, tiles, units;
   size_t plane_bytes, a_stage_bytes, wslab, wbytes, smem, tab_bytes;
 };
 
@@ -145,7 +146,23 @@ Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride, int mod
     g.wst = (int)(slots > 16 ? 16 : slots);
   }
   g.smem = HDR_BYTES + g.tab_bytes + g.nastage * g.a_stage_bytes + (g.w_resident ? g.wbytes : (size_t)g.wst * g.spb * g.wslab);
-  g.grid = (int)(g.tiles < 148 ? g.tiles : 148);
+  // Split-K over the filter taps for launches that under-fill the 148 SMs (stage-4 144->144 at 8x8: 50 tiles, 81 K steps each;
+  // 72->72 at 16x16: 162 tiles = two rounds for 14 CTAs): a work unit is (tile, half of the taps), the two halves are added with
+  // fp32 atomics onto a zeroed output.  With exactly TWO addends the result does not depend on their order (0 + a = a exactly,
+  // a + b = b + a), so the forward stays bit-reproducible.  Taken when it shortens the critical path in rounds of work units.
+  // MEASURED (B200, round 2): not a win as built — 8x8 144->144 B=64 34.7 us (36.6 without), 16x16 72->72 41.3 us (32.7
+  // without), step 90.7 ms vs 87.0: both halves re-stage the whole halo, the scalar fp32 atomics of the epilogue and the extra
+  // memset cost more than the shorter K loop saves, and the weight ring (not the MMA count) bounds these layers: every CTA
+  // streams its slabs from L2 at ~21 B/clk (5 chunks in flight).  Off unless HCM_TC_KSPLIT=1 (kept for experiments).
+  g.ksplit = 1;
+  static int ks_on = -1;
+  if (ks_on < 0) { const char* e = getenv("HCM_TC_KSPLIT"); ks_on = (e && e[0] == '1') ? 1 : 0; }
+  if (ks_on == 1 && mode == 0 && !g.rc && g.taps == 9 && g.nsteps >= 18) {
+    const long r1 = (g.tiles + 147) / 148, r2 = (2 * g.tiles + 147) / 148;
+    if (r2 < 2 * r1) g.ksplit = 2;
+  }
+  g.units = g.tiles * g.ksplit;
+  g.grid = (int)(g.units < 148 ? g.units : 148);
   return g;
 }
 
@@ -172,7 +189,8 @@ struct TcParams {
   // host-built issue schedule: steps ordered (group, tap, K16 step); x = byte offset of the A operand inside a stage,
   // y = weight slab index.  The MMA warp reads it from the constant bank (uniform loads): the issue loop must stay lean,
   // a tcgen05.mma of N<=64 retires in ~40-48 cycles (measured) and integer address math per step would dominate.
-  int gcount[MAXG];
+  int gcount[2][MAXG];         // steps of (part, group); part = half of the filter taps when g.ksplit == 2
+  int pstart[2], plen[2];      // first schedule step / number of steps of a part
   uint2 steps[MAX_STEPS];
 };
 
@@ -192,23 +210,31 @@ __host__ __device__ __forceinline__ void tap_info(const Geo& g, int tap, int& q,
 void build_steps(TcParams& p) {
   const Geo& g = p.g;
   const int nj = g.Cin16 / 16;
+  const int ntap = g.rc ? 3 : g.taps;
   int n = 0;
-  for (int grp = 0; grp < g.ngroups; ++grp) {
-    const int c_lo = grp * g.cg, c_hi = c_lo + g.cg;
-    p.gcount[grp] = 0;
-    for (int tap = 0; tap < (g.rc ? 3 : g.taps); ++tap) {
-      int q, rowoff;
-      if (g.rc) { q = 0; rowoff = tap * g.Wp; }          // one step per filter row: its three taps are N blocks of the operand
-      else tap_info(g, tap, q, rowoff);
-      for (int j = 0; j < nj; ++j) {
-        const int cs = q * g.Cin16 + 16 * j;
-        if (cs < c_lo || cs >= c_hi) continue;
-        const int cl = cs - c_lo;
-        p.steps[n].x = (uint32_t)(cl / g.KB) * (uint32_t)g.plane_bytes + (uint32_t)rowoff * g.SW + (uint32_t)(cl % g.KB) * 2;
-        p.steps[n].y = (uint32_t)(tap * nj + j);
-        ++n; ++p.gcount[grp];
+  for (int part = 0; part < 2; ++part) {
+    // taps of this part: all of them, or the first 5 / last 4 of the 9
+    const int t_lo = (g.ksplit == 2) ? (part == 0 ? 0 : (ntap + 1) / 2) : (part == 0 ? 0 : ntap);
+    const int t_hi = (g.ksplit == 2) ? (part == 0 ? (ntap + 1) / 2 : ntap) : ntap;
+    p.pstart[part] = n;
+    for (int grp = 0; grp < g.ngroups; ++grp) {
+      const int c_lo = grp * g.cg, c_hi = c_lo + g.cg;
+      p.gcount[part][grp] = 0;
+      for (int tap = t_lo; tap < t_hi; ++tap) {
+        int q, rowoff;
+        if (g.rc) { q = 0; rowoff = tap * g.Wp; }          // one step per filter row: its three taps are N blocks of the operand
+        else tap_info(g, tap, q, rowoff);
+        for (int j = 0; j < nj; ++j) {
+          const int cs = q * g.Cin16 + 16 * j;
+          if (cs < c_lo || cs >= c_hi) continue;
+          const int cl = cs - c_lo;
+          p.steps[n].x = (uint32_t)(cl / g.KB) * (uint32_t)g.plane_bytes + (uint32_t)rowoff * g.SW + (uint32_t)(cl % g.KB) * 2;
+          p.steps[n].y = (uint32_t)(tap * nj + j);
+          ++n; ++p.gcount[part][grp];
+        }
       }
     }
+    p.plen[part] = n - p.pstart[part];
   }
 }
 
@@ -275,7 +301,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + 512);
   float* s_sc = reinterpret_cast<float*>(smem + 1024);
   float* s_sh = s_sc + 256;
-  int* s_unit = reinterpret_cast<int*>(smem + 4096);                     // per group: packed (q, src channel, staged byte)
+  uint2* s_steps = reinterpret_cast<uint2*>(smem + 4096 + 6144);         // resident weights: per step (A offset >> 4, B descriptor low word)
   int* s_src = reinterpret_cast<int*>(smem + HDR_BYTES);                 // [nastage][Lpad][nq] source pixel or -1
   const int tab_stride = (int)(g.tab_bytes / g.nastage / 4);
   uint8_t* Abase = smem + HDR_BYTES + g.tab_bytes;
@@ -297,6 +323,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     for (int s = 0; s < 16; ++s) { mbar_init(BAR(16 + s), 1); mbar_init(BAR(32 + s), 1); }
     fence_mbar_init();
   }
+  if (g.w_resident) {
+    // issue schedule as descriptor LOW WORDS (see umma_bf16_w): the MMA warp then needs one add per operand and step
+    const uint32_t b_lo32 = (uint32_t)smem_desc(0, (uint32_t)(2 * g.NB) * 16, 128);
+    const uint32_t w0s = smem_u32(smem + HDR_BYTES + g.tab_bytes + (size_t)g.nastage * g.a_stage_bytes);
+    for (int i = threadIdx.x; i < g.nsteps; i += NTHREADS)
+      s_steps[i] = make_uint2(p.steps[i].x >> 4, b_lo32 + ((w0s + p.steps[i].y * (uint32_t)g.wslab) >> 4));
+  }
   for (int c = threadIdx.x; c < 256; c += NTHREADS) {
     s_sc[c] = (p.in_scale && c < p.Cin) ? p.in_scale[c] : 1.f;
     s_sh[c] = (p.in_scale && c < p.Cin) ? p.in_shift[c] : 0.f;
@@ -311,8 +344,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
 
-  const int my_tiles = (int)((g.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const int my_tiles = (int)((g.units - blockIdx.x + gridDim.x - 1) / gridDim.x);   // work units (tile, part) of this CTA
+  const int ksplit = g.ksplit;
   const int nj = g.Cin16 / 16;                                           // K=16 steps per tap
+  (void)nj;
 
   if (warp == W_TMA) {
     // ===== TMA producer: weight slabs in the order the MMA warp consumes them =====
@@ -326,16 +361,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
       } else {
         long it = 0;                                                     // chunk counter
         const uint32_t chunk_bytes = (uint32_t)g.spb * wslab;
-        for (int ti = 0; ti < my_tiles; ++ti)
-          for (int st0 = 0; st0 < g.nsteps; st0 += g.spb, ++it) {
+        for (int ti = 0; ti < my_tiles; ++ti) {
+          const int part = (int)(((long)blockIdx.x + (long)ti * gridDim.x) % ksplit);
+          const int st_end = p.pstart[part] + p.plen[part];
+          for (int st0 = p.pstart[part]; st0 < st_end; st0 += g.spb, ++it) {
             const int s = (int)(it % g.wst);
-            const int n = min(g.spb, g.nsteps - st0);
+            const int n = min(g.spb, st_end - st0);
             mbar_wait(BAR(32 + s), (uint32_t)(((it / g.wst) & 1) ^ 1));
             mbar_expect_tx(BAR(16 + s), (uint32_t)n * wslab);
             for (int k = 0; k < n; ++k)
               tma_bulk_g2s(smem_u32(Wbase + (size_t)s * chunk_bytes + (size_t)k * wslab),
                            p.wpack + (size_t)p.steps[st0 + k].y * wslab, wslab, BAR(16 + s));
           }
+        }
       }
     }
   } else if (warp == W_MMA) {
@@ -358,7 +396,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
       tc_fence_after();
       const uint32_t d = tmem + (uint32_t)(as * g.acc_cols);
       uint32_t first = 0;                 // accumulate flag of the next MMA (0 = overwrite: first MMA of the tile)
-      int sidx = 0;
+      const int part = (int)(((long)blockIdx.x + (long)ti * gridDim.x) % ksplit);
+      int sidx = p.pstart[part];
+      const int st_end = sidx + p.plen[part];
       for (int grp = 0; grp < g.ngroups; ++grp, ++f) {
         const int s = (int)(f % g.nastage);
         tq = clock64();
@@ -366,28 +406,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
         c_a += clock64() - tq;
         tc_fence_after();
         const uint32_t ab = a0 + (uint32_t)s * (uint32_t)g.a_stage_bytes;
-        const int n = p.gcount[grp];
+        const int n = p.gcount[part][grp];
         if (g.w_resident) {
           if (elect_one()) {
-            for (int k = 0; k < n; ++k, ++sidx) {
-              const uint2 stp = p.steps[sidx];
-              const uint32_t arow = ab + stp.x, wb = w0 + stp.y * wslab;
-              const uint64_t ah = a_t | (uint64_t)(arow >> 4), al = a_t | (uint64_t)((arow + lo_off) >> 4);
-              const uint64_t bw = b_t | (uint64_t)(wb >> 4);
-              if (g.concat) {
-                umma_bf16(d, ah, bw, idesc_2n, first);                      // [A_hi*w_hi | A_hi*w_lo]
-                umma_bf16(d, al, bw, idesc_n, 1u);                          // += A_lo*w_hi (first Np rows of the slab)
-              } else {
-                umma_bf16(d, ah, bw, idesc_n, first);
-                umma_bf16(d, ah, bw + (uint64_t)(g.NB), idesc_n, 1u);     // lo rows start Npad*16 bytes further
-                umma_bf16(d, al, bw, idesc_n, 1u);
+            // lean issue loop: descriptor low words = per-stage base + per-step offset (one add per operand), shared high words
+            const uint32_t a_hi32 = (uint32_t)(a_t >> 32), b_hi32 = (uint32_t)(b_t >> 32);
+            const uint32_t abl = (uint32_t)a_t + (ab >> 4), lo16 = lo_off >> 4, nb = (uint32_t)g.NB;
+            const uint2* st = s_steps + sidx;
+            if (g.concat) {
+#pragma unroll 4
+              for (int k = 0; k < n; ++k) {
+                const uint2 stp = st[k];
+                const uint32_t ah = abl + stp.x;
+                umma_bf16_w(d, ah, a_hi32, stp.y, b_hi32, idesc_2n, (k | first) ? 1u : 0u);   // [A_hi*w_hi | A_hi*w_lo]
+                umma_bf16_acc(d, ah + lo16, a_hi32, stp.y, b_hi32, idesc_n);                   // += A_lo*w_hi (first Np rows of the slab)
               }
-              first = 1u;
+            } else {
+#pragma unroll 2
+              for (int k = 0; k < n; ++k) {
+                const uint2 stp = st[k];
+                const uint32_t ah = abl + stp.x;
+                umma_bf16_w(d, ah, a_hi32, stp.y, b_hi32, idesc_n, (k | first) ? 1u : 0u);
+                umma_bf16_acc(d, ah, a_hi32, stp.y + nb, b_hi32, idesc_n);                     // lo rows start Npad*16 bytes further
+                umma_bf16_acc(d, ah + lo16, a_hi32, stp.y, b_hi32, idesc_n);
+              }
             }
-          } else {
-            sidx += n;
           }
-          first = 1u;
+          sidx += n;
+          if (n) first = 1u;
         } else {
           for (int k = 0; k < n; ++k, ++sidx) {
             if (within == 0 || k == 0) {
@@ -398,7 +444,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
             const uint32_t arow = ab + stp.x, wb = w0 + (uint32_t)(rs * g.spb + within) * wslab;
             const uint64_t ah = a_t | (uint64_t)(arow >> 4), al = a_t | (uint64_t)((arow + lo_off) >> 4);
             const uint64_t bw = b_t | (uint64_t)(wb >> 4);
-            const bool last = (within == g.spb - 1) || (sidx == g.nsteps - 1);
+            const bool last = (within == g.spb - 1) || (sidx == st_end - 1);
             if (elect_one()) {
               if (g.concat) {
                 umma_bf16(d, ah, bw, idesc_2n, first);
@@ -432,7 +478,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     for (long f = team; f < nfills; f += g.nastage) {
       {
         const int ti = (int)(f / g.ngroups), grp = (int)(f - (long)ti * g.ngroups);
-        const long tile0 = ((long)blockIdx.x + (long)ti * gridDim.x) * g.TM;
+        const long tile0 = (((long)blockIdx.x + (long)ti * gridDim.x) / ksplit) * g.TM;
         const int s = team;
         tq = clock64();
         mbar_wait(BAR(4 + s), (uint32_t)(((f / g.nastage) & 1) ^ 1));
@@ -466,7 +512,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     long long c_wait = 0, c_all = clock64(), tq;
     const bool vec4 = (p.Cout % 4) == 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
-      const long tile0 = ((long)blockIdx.x + (long)ti * gridDim.x) * g.TM;
+      const long unit = (long)blockIdx.x + (long)ti * gridDim.x;
+      const long tile0 = (unit / ksplit) * g.TM;
+      const bool atomic_out = ksplit > 1;                 // split-K: both halves are added onto the zeroed / accumulated output
+      const bool add_bias = p.bias && (unit % ksplit) == 0;
       const int as = ti % g.acc_stages;
       const int px = (m < g.TM) ? virt_to_dst(tile0 + m, p) : -1;   // row-concat tiles: rows 126, 127 belong to the next tile
       float* yp = p.y + (long)(px < 0 ? 0 : px) * p.Cout;   // indexed [c0 + i] below
@@ -525,11 +574,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
         }
         const int cend = (g.mode == 1) ? (c0 / g.Cp) * g.Cp + p.Cout : p.Cout;      // first invalid column
         if (px >= 0) {
-          if (p.bias) {
+          if (add_bias) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) if (c0 + i < cend) v[i] += p.bias[c0 + i];
           }
-          if (vec4) {
+          if (atomic_out) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (c0 + i < cend) atomicAdd(yp + c0 + i, v[i]);
+          } else if (vec4) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
               if (c0 + i < cend) {
@@ -711,7 +763,7 @@ int launch_tc(TcParams& p, cudaStream_t stream, const char* what) {
     const long long* o = h;      // CTA 0
     fprintf(stderr, "[%s dbg] %dx%d %d->%d mode %d tiles/cta %ld steps %d astages %d resident %d | mma: total %lld wait_acc %lld "
             "wait_a %lld | transform: total %lld wait %lld | epilogue: total %lld wait %lld\n", what, p.H, p.W, p.Cin, p.Cout,
-            p.g.mode, (p.g.tiles + p.g.grid - 1) / p.g.grid, p.g.nsteps, p.g.nastage, p.g.w_resident, o[0], o[2], o[3], o[4],
+            p.g.mode, (p.g.units + p.g.grid - 1) / p.g.grid, p.g.nsteps, p.g.nastage, p.g.w_resident, o[0], o[2], o[3], o[4],
             o[5], o[6], o[7]);
   }
   return HCM_OK;
@@ -825,6 +877,10 @@ int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, 
   p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.in_relu = in_relu;
   p.wpack = reinterpret_cast<const uint8_t*>(wpack); p.bias = bias; p.y = y; p.accumulate = accumulate;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.q0 = 0;
+  if (p.g.ksplit > 1 && !accumulate) {
+    cudaError_t e = cudaMemsetAsync(y, 0, (size_t)B * p.g.Ho * p.g.Wo * Cout * sizeof(float), stream);
+    if (e != cudaSuccess) { hcm_set_error("tc_conv: memset: %s", cudaGetErrorString(e)); return HCM_ERR_CUDA; }
+  }
   return launch_tc(p, stream, "tc_conv");
 }
 

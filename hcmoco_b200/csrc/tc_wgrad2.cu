@@ -208,6 +208,12 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
     }
     __syncwarp();
     long long c_all = clock64(), c_wait = 0, tq;
+    // lean issue loop (see umma_bf16_w in tc_common.cuh): descriptor low words = stage base + K-step offset + tap offset
+    const uint32_t dy_hi32 = (uint32_t)(dy_t >> 32), a_hi32 = (uint32_t)(a_t >> 32);
+    const uint32_t dlo16 = d_lo >> 4, alo16 = a_lo >> 4, kd16 = (16u * SWd) >> 4, ka16 = (16u * SWa) >> 4;
+    uint32_t boff16[9], dcolv[9];
+#pragma unroll
+    for (int m = 0; m < 9; ++m) { boff16[m] = tap_boff[m] >> 4; dcolv[m] = tmem + tap_col[m]; }
     for (int it = 0; it < ntiles; ++it) {
       const int s = it % g.nstage;
       tq = clock64();
@@ -215,24 +221,33 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
       c_wait += clock64() - tq;
       tc_fence_after();
       const uint32_t st = s0 + (uint32_t)s * (uint32_t)g.stage_bytes;
-      for (int k = 0; k < TILE / 16; ++k) {
-        const uint32_t dyk = st + (uint32_t)k * 16u * SWd;
-        const uint64_t dyh = dy_t | (uint64_t)(dyk >> 4), dyl = dy_t | (uint64_t)((dyk + d_lo) >> 4);
-        const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
-        const uint32_t abase = st + a_off + (uint32_t)k * 16u * SWa;
-        for (int m = 0; m < nmma; ++m) {
-          // operand B start: halo row of this K step + tap shift (+ parity plane for stride 2); D column block
-          const uint32_t ak = abase + tap_boff[m];
-          const uint64_t ah = a_t | (uint64_t)(ak >> 4), al = a_t | (uint64_t)((ak + a_lo) >> 4);
-          const uint32_t dcol = tmem + tap_col[m];
-          if (elect_one()) {
-            umma_bf16(dcol, dyh, ah, idesc, acc);
-            umma_bf16(dcol, dyh, al, idesc, 1u);
-            if (!fold) umma_bf16(dcol, dyl, ah, idesc, 1u);
+      if (elect_one()) {
+        uint32_t dyh = (uint32_t)dy_t + (st >> 4), ab = (uint32_t)a_t + ((st + a_off) >> 4);
+        for (int k = 0; k < TILE / 16; ++k, dyh += kd16, ab += ka16) {
+          const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+          if (nmma == 3) {
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+              const uint32_t ah = ab + boff16[m];
+              umma_bf16_w(dcolv[m], dyh, dy_hi32, ah, a_hi32, idesc, acc);
+              umma_bf16_acc(dcolv[m], dyh, dy_hi32, ah + alo16, a_hi32, idesc);
+              if (!fold) umma_bf16_acc(dcolv[m], dyh + dlo16, dy_hi32, ah, a_hi32, idesc);
+            }
+          } else {
+#pragma unroll
+            for (int m = 0; m < 9; ++m) {
+              if (m < nmma) {
+                const uint32_t ah = ab + boff16[m];
+                umma_bf16_w(dcolv[m], dyh, dy_hi32, ah, a_hi32, idesc, acc);
+                umma_bf16_acc(dcolv[m], dyh, dy_hi32, ah + alo16, a_hi32, idesc);
+                if (!fold) umma_bf16_acc(dcolv[m], dyh + dlo16, dy_hi32, ah, a_hi32, idesc);
+              }
+            }
           }
         }
+        umma_commit(BAR(4 + s));
       }
-      if (elect_one()) umma_commit(BAR(4 + s));
+      __syncwarp();
     }
     if (elect_one()) umma_commit(BAR(8));
     if (p.dbg && lane == 0) { long long* o = p.dbg + (long)blockIdx.x * 8; o[0] = clock64() - c_all; o[1] = c_wait; }
