@@ -99,16 +99,27 @@ Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride, int mod
   g.SW = (g.SC <= 32) ? 64 : 128;             // bytes per staged row block = swizzle span
   g.KB = g.SW / 2;
   g.plane_bytes = (size_t)g.Lpad * g.SW;
-  // channel groups: one A stage holds `cg` staged channels (hi + lo planes), a multiple of KB when there are several
+  g.NB = g.rc ? 3 * g.Npad : g.Npad;
+  g.nsteps = (g.rc ? 3 : g.taps) * (g.Cin16 / 16);
+  g.wslab = (size_t)64 * g.NB;                // [2 K-chunks][2*NB rows: hi then lo][16 B]
+  g.wbytes = (size_t)g.nsteps * g.wslab;
+  const size_t tab1 = (size_t)ceil_to(g.Lpad * g.nq * 4, 1024);           // source-pixel table of one stage
+  const size_t wmin = g.wbytes < 8 * g.wslab ? g.wbytes : 8 * g.wslab;
+  const size_t total = 225 * 1024 - HDR_BYTES;
+  // channel groups: one A stage holds `cg` staged channels (hi + lo planes), a multiple of KB when there are several.
+  // As many blocks per group as 84 KB hold, but never so many that only ONE stage fits beside a minimal weight ring: with a
+  // single stage the fill of group g+1 waits for the MMAs of group g (measured, 8x8 144->144: fill 5k -> MMA 15k -> fill 5k ->
+  // MMA 2k cycles, strictly serial); two smaller stages let the fills run side by side / under the MMAs.
   int max_blk = (int)((84 * 1024) / (2 * g.plane_bytes));
   if (max_blk < 1) max_blk = 1;
   const int nblk_all = (g.SC + g.KB - 1) / g.KB;
-  g.ngroups = (nblk_all + max_blk - 1) / max_blk;
-  g.nblk = (nblk_all + g.ngroups - 1) / g.ngroups;
+  for (;; --max_blk) {
+    g.ngroups = (nblk_all + max_blk - 1) / max_blk;
+    g.nblk = (nblk_all + g.ngroups - 1) / g.ngroups;
+    g.a_stage_bytes = (size_t)2 * g.nblk * g.plane_bytes;
+    if (max_blk == 1 || 2 * (g.a_stage_bytes + tab1) + wmin <= total) break;
+  }
   g.cg = g.nblk * g.KB;
-  g.NB = g.rc ? 3 * g.Npad : g.Npad;
-  g.nsteps = (g.rc ? 3 : g.taps) * (g.Cin16 / 16);
-  g.a_stage_bytes = (size_t)2 * g.nblk * g.plane_bytes;
   // (row-concat keeps hi and lo weights as separate operands: the epilogue then reads 3, not 6, accumulator blocks per chunk)
   g.concat = (!g.rc && 2 * g.NB <= 256) ? 1 : 0;
   g.acc_cols = g.concat ? 2 * g.NB : g.NB;
@@ -116,13 +127,8 @@ Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride, int mod
   int c = 32;
   while (c < g.acc_stages * g.acc_cols) c <<= 1;
   g.tmem_cols = c;
-  g.wslab = (size_t)64 * g.NB;                // [2 K-chunks][2*NB rows: hi then lo][16 B]
-  g.wbytes = (size_t)g.nsteps * g.wslab;
   // A stages: each is filled by its own team of transform warps, so several halo gathers are in flight at once (the
   // gather of a narrow layer is pure latency: ~5 loads per thread); 2..4 stages as shared memory allows
-  const size_t tab1 = (size_t)ceil_to(g.Lpad * g.nq * 4, 1024);           // source-pixel table of one stage
-  const size_t wmin = g.wbytes < 8 * g.wslab ? g.wbytes : 8 * g.wslab;
-  const size_t total = 225 * 1024 - HDR_BYTES;
   g.nastage = 1;
   for (int n = MAX_ASTAGE; n >= 2; n >>= 1) {      // 4 or 2: teams of NTRANS/n threads (whole warps)
     const size_t w = (g.wbytes + n * (g.a_stage_bytes + tab1) <= total) ? g.wbytes : wmin;   // prefer resident weights
@@ -323,8 +329,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     for (int s = 0; s < 16; ++s) { mbar_init(BAR(16 + s), 1); mbar_init(BAR(32 + s), 1); }
     fence_mbar_init();
   }
-  if (g.w_resident) {
+  {
     // issue schedule as descriptor LOW WORDS (see umma_bf16_w): the MMA warp then needs one add per operand and step
+    // (.y = B descriptor of the step's slab when the weights are resident; the ring computes it from the slot)
     const uint32_t b_lo32 = (uint32_t)smem_desc(0, (uint32_t)(2 * g.NB) * 16, 128);
     const uint32_t w0s = smem_u32(smem + HDR_BYTES + g.tab_bytes + (size_t)g.nastage * g.a_stage_bytes);
     for (int i = threadIdx.x; i < g.nsteps; i += NTHREADS)
@@ -435,30 +442,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
           sidx += n;
           if (n) first = 1u;
         } else {
-          for (int k = 0; k < n; ++k, ++sidx) {
-            if (within == 0 || k == 0) {
-              mbar_wait(BAR(16 + rs), rph);                                // (re-waiting a completed phase is harmless)
-              tc_fence_after();
-            }
-            const uint2 stp = p.steps[sidx];
-            const uint32_t arow = ab + stp.x, wb = w0 + (uint32_t)(rs * g.spb + within) * wslab;
-            const uint64_t ah = a_t | (uint64_t)(arow >> 4), al = a_t | (uint64_t)((arow + lo_off) >> 4);
-            const uint64_t bw = b_t | (uint64_t)(wb >> 4);
-            const bool last = (within == g.spb - 1) || (sidx == st_end - 1);
+          // weight ring, lean: one barrier wait per chunk of `spb` steps, then the chunk's steps are issued by the elected lane
+          // with descriptor low words (A: stage base + per-step offset from s_steps; B: ring slot, advancing one slab per step)
+          const uint32_t a_hi32 = (uint32_t)(a_t >> 32), b_hi32 = (uint32_t)(b_t >> 32);
+          const uint32_t abl = (uint32_t)a_t + (ab >> 4), lo16 = lo_off >> 4, nb = (uint32_t)g.NB, ws16 = wslab >> 4;
+          const uint32_t bbase = (uint32_t)b_t + (w0 >> 4);
+          int k = 0;
+          while (k < n) {
+            mbar_wait(BAR(16 + rs), rph);                                  // (re-waiting a completed phase is harmless)
+            tc_fence_after();
+            const int m = min(n - k, g.spb - within);                      // steps of this group inside the current chunk
+            const bool done = (within + m == g.spb) || (sidx + m == st_end);
             if (elect_one()) {
+              uint32_t wbl = bbase + (uint32_t)(rs * g.spb + within) * ws16;
+              const uint2* st = s_steps + sidx;
               if (g.concat) {
-                umma_bf16(d, ah, bw, idesc_2n, first);
-                umma_bf16(d, al, bw, idesc_n, 1u);
+                for (int i = 0; i < m; ++i, wbl += ws16) {
+                  const uint32_t ah = abl + st[i].x;
+                  umma_bf16_w(d, ah, a_hi32, wbl, b_hi32, idesc_2n, (i | k | first) ? 1u : 0u);
+                  umma_bf16_acc(d, ah + lo16, a_hi32, wbl, b_hi32, idesc_n);
+                }
               } else {
-                umma_bf16(d, ah, bw, idesc_n, first);
-                umma_bf16(d, ah, bw + (uint64_t)(g.NB), idesc_n, 1u);
-                umma_bf16(d, al, bw, idesc_n, 1u);
+                for (int i = 0; i < m; ++i, wbl += ws16) {
+                  const uint32_t ah = abl + st[i].x;
+                  umma_bf16_w(d, ah, a_hi32, wbl, b_hi32, idesc_n, (i | k | first) ? 1u : 0u);
+                  umma_bf16_acc(d, ah, a_hi32, wbl + nb, b_hi32, idesc_n);
+                  umma_bf16_acc(d, ah + lo16, a_hi32, wbl, b_hi32, idesc_n);
+                }
               }
-              if (last) umma_commit(BAR(32 + rs));
+              if (done) umma_commit(BAR(32 + rs));
             }
-            if (last) { within = 0; if (++rs == g.wst) { rs = 0; rph ^= 1u; } } else { ++within; }
-            first = 1u;
+            __syncwarp();
+            k += m; sidx += m; within += m;
+            if (done) { within = 0; if (++rs == g.wst) { rs = 0; rph ^= 1u; } }
           }
+          if (n) first = 1u;
         }
         if (elect_one()) umma_commit(BAR(4 + s));                         // staged A buffer free
       }
