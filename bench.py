@@ -239,10 +239,11 @@ def dense_affinity_roofline(K, hbm_peak, B=32, h=64, S=400, reps=20):
     use_depth = torch.ones(B, dtype=torch.int64, device="cuda")
     stat, fin = torch.zeros(B, 2, S, 4, device="cuda"), torch.zeros(8, device="cuda")
     d1, d2 = torch.zeros_like(G1), torch.zeros_like(G2)
+    work = torch.empty((K.dense_affinity_work_bytes(B, S) + 3) // 4, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2: evict the maps between launches
     out = {}
-    for name, fn in (("dense_affinity_fwd", lambda: K.dense_affinity_fwd(G1, G2, pix, kept, use_depth, B, S, h, 128, 1 / 0.07, stat, fin)),
-                     ("dense_affinity_bwd", lambda: K.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1 / 0.07, 1.0, 1.0, d1, d2))):
+    for name, fn in (("dense_affinity_fwd", lambda: K.dense_affinity_fwd(G1, G2, pix, kept, use_depth, B, S, h, 128, 1 / 0.07, stat, fin, work)),
+                     ("dense_affinity_bwd", lambda: K.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1 / 0.07, 1.0, 1.0, d1, d2, work, 0))):
         fn()
         ts = []
         for _ in range(reps):

@@ -3,20 +3,26 @@
 //   a_j = norm(G1[b, pix_j, :])   d_i = norm(G2[b, pix_i, :])   L[i][j] = <d_i, a_j> / T      (S sampled pixels, C = 128)
 //   loss_r2d = -mean_j sum_i W[i][j] log_softmax_i L[i][j]      loss_d2r = the same on L^T     W = softmax_i(-|c_i - c_j|)
 //
-// One CTA owns (sample b, side, strip of <=128 rows).  side 0: strip rows are the a_j (statistics of the COLUMNS of L),
-// the other operand is all d_i; side 1: strip rows are the d_i (statistics of the ROWS of L), the other operand all a_j.
-// Computing both L-strips and L^T-strips on the tensor cores makes every softmax statistic a per-row (= per TMEM lane)
-// reduction: no cross-lane shuffles, no cross-CTA combine, and nothing S x S is ever written to HBM.
+// Two kernels per direction of the chain rule:
+//   dense_prep_kernel   gathers the S sampled pixels of both maps ONCE per sample (512-B coalesced rows of the channels-last
+//                       maps), L2-normalises, splits into bf16 hi / lo and writes them as ready-made UMMA operand slabs
+//                       ([chunk of NC rows][channel/8][row][8 channels], K-major no-swizzle) into a caller-owned workspace;
+//   dense_affinity_kernel  one CTA per (sample, side, strip of NC <= 128 rows).  side 0: strip rows are the a_j (statistics of
+//                       the COLUMNS of L), the other operand is all d_i; side 1: strip rows are the d_i (statistics of the ROWS
+//                       of L).  Slabs arrive by TMA (cp.async.bulk, one per slab, double-buffered in the forward); S x S x 128
+//                       on tcgen05 (hi*hi + lo*hi + hi*lo, fp32 in TMEM, two accumulators in the forward so the MMAs of chunk
+//                       c+1 run under the epilogue of chunk c); epilogue on 16 warps: soft-target log-softmax statistics
+//                       (forward) or the logit gradient G, which goes back to shared memory as the A operand of a second MMA
+//                       dXn = G * Y (the Y slab re-read in place as an MN-major B operand), then the L2-norm backward and a
+//                       coalesced atomic scatter into the map gradient (sampled pixels repeat).
+// Computing both L-strips and L^T-strips makes every softmax statistic a per-row (= per TMEM lane) reduction: no cross-lane
+// shuffles, no cross-CTA combine, and nothing S x S is ever written to HBM.
+// Round 2: before the split into prep + TMA-fed main kernel every strip re-gathered and re-normalised the whole other operand
+// (40 % of the 18 M warp instructions of a forward launch, ncu), and the epilogue used the accurate sqrtf / a branchy online
+// softmax (115 instructions per 32 logits); forward 103 -> see DESIGN.md for the measured times.
 //
-//   gather (512 B coalesced rows of the channels-last maps) -> L2-normalise -> bf16 hi/lo split -> shared memory in the
-//   UMMA no-swizzle K-major layout -> tcgen05.mma (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM) per chunk of NC
-//   columns -> tcgen05.ld epilogue: online soft-target log-softmax statistics (forward) or the logit gradient
-//   G = coef*(softmax_own + softmax_other - W_own - W_other), which goes back to shared memory as the A operand of a second
-//   MMA  dXn = G * Y  (Y re-used in place as an MN-major B operand), then the L2-norm backward and a coalesced
-//   atomic scatter into the map gradient (sampled pixels repeat).
-//
-// Algorithmic HBM bytes per depth-bearing triplet: 2*S*128*4 gathered features (+2*S*8 indices); the redundant re-gathers of
-// the "other" operand by the strips of a sample hit L2.
+// Algorithmic HBM bytes per depth-bearing triplet: 2*S*128*4 gathered features (+2*S*8 indices); the slabs (same size, bf16 hi+lo)
+// are written once and re-read from L2.
 #include "tc_common.cuh"
 
 namespace {
@@ -27,28 +33,30 @@ constexpr int DA_PARTS = DA_THREADS / 128;  // column parts of the epilogue (one
 constexpr int DA_HDR = 1024;
 
 struct DaGeo {
-  int S, h, HW, nstrips, RS, nchunks, NC, Spad;
-  uint32_t lbo_x, lbo_y;            // K-direction core-matrix strides (bytes) of the strip / chunk slabs
+  int S, h, HW, nch, NC, Spad;
+  uint32_t lbo, lbo_g;              // K-direction core-matrix strides (bytes): operand slabs (NC rows) / gradient slab (128 rows)
+  uint32_t half, slab;              // bytes of the hi (= lo) part / of one slab
   uint32_t off_tab, off_red, off_x, off_y, off_g, smem_bytes;
 };
 
 DaGeo da_geo(int S, int h, bool bwd) {
   DaGeo g;
   g.S = S; g.h = h; g.HW = h * h;
-  g.nstrips = (S + 127) / 128;
-  g.RS = (S + g.nstrips - 1) / g.nstrips;
-  g.nchunks = (S + 127) / 128;
-  g.NC = ceil_to((S + g.nchunks - 1) / g.nchunks, 16);
-  g.Spad = g.nchunks * g.NC;
-  g.lbo_x = 128 * 16 + 16;
-  g.lbo_y = (uint32_t)g.NC * 16 + 16;
+  g.nch = (S + 127) / 128;                                        // strips of rows = chunks of columns
+  g.NC = ceil_to((S + g.nch - 1) / g.nch, 16);
+  g.Spad = g.nch * g.NC;
+  g.lbo = (uint32_t)g.NC * 16 + 16;
+  g.lbo_g = 128 * 16 + 16;
+  g.half = 16 * g.lbo;
+  g.slab = 2 * g.half;
   uint32_t o = DA_HDR;
   g.off_tab = o; o += (uint32_t)g.Spad * 5 * 4;                  // cy, cx, lse_other, zinv_other, pixel offset
   g.off_red = o; o += DA_PARTS * 128 * 8 * 4;
   o = (o + 127) / 128 * 128;
-  g.off_x = o; o += 2 * 16 * g.lbo_x;                            // X hi | X lo   (also the fp32 staging of the scatter)
-  g.off_y = o; o += 2 * 16 * g.lbo_y;                            // Y hi | Y lo
-  g.off_g = o; if (bwd) o += 2 * (uint32_t)(g.NC / 8) * g.lbo_x; // G hi | G lo
+  g.off_x = o; o += g.slab;                                      // X hi | X lo   (+ the following Y slab: fp32 staging of the scatter)
+  g.off_y = o; o += (bwd ? 1 : 2) * g.slab;                      // Y hi | Y lo, double-buffered in the forward
+  g.off_g = o; if (bwd) o += 2 * (uint32_t)(g.NC / 8) * g.lbo_g; // G hi | G lo
+  if (bwd && o < g.off_x + 128 * 129 * 4) o = g.off_x + 128 * 129 * 4;
   g.smem_bytes = o;
   return g;
 }
@@ -58,6 +66,7 @@ struct DaParams {
   const long long* pix; const float* kept; const float* fin;
   float* stat;                     // [B][2][S][4] = (lse, Z, sum w*logit, first-argmax hit)
   float* dG1; float* dG2;
+  uint8_t* work;                   // [B][2][nch][slab]: operand slabs written by dense_prep_kernel
   float inv_T, gscale, gscale_o;     // gscale: d(total)/d(loss_r2d), gscale_o: d(total)/d(loss_d2r)
   DaGeo g;
 };
@@ -83,39 +92,44 @@ __device__ __forceinline__ uint32_t da_idesc(int N, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-// Stage rows [first, first + nrows) of one sample (row r valid if first + r < last): gather 128 channels from the
-// channels-last map (s_off[row] = element offset of the sampled pixel), L2-normalise (F.normalize, eps 1e-12), split into
-// bf16 hi / lo, write both K-major slabs ([channel/8][row][8 channels], chunk stride lbo).  One warp per row (512 B
-// coalesced), 8 rows in flight per warp: the gather is pure latency, so it is split in two — `da_load` issues the loads of a
-// slab (nrows <= 128 = 16 warps x 8 rows) into registers, `da_store` normalises and writes them — and the loads of chunk c+1
-// are issued right after the MMAs of chunk c, so that their latency hides under that chunk's MMAs and epilogue.
-constexpr int DA_U = 8;
-struct DaRows { float4 v[DA_U]; };
-
-__device__ __forceinline__ void da_load(const float* __restrict__ map_b, const int* __restrict__ s_off, int first, int last,
-                                        int nrows, DaRows& R, int warp, int lane) {
-#pragma unroll
-  for (int u = 0; u < DA_U; ++u) {
-    const int r = warp * DA_U + u, gr = first + r;
-    R.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < nrows && gr < last) R.v[u] = __ldg(reinterpret_cast<const float4*>(map_b + s_off[gr] + 4 * lane));
+// One warp per sampled pixel q of (sample b, map m): 512-B coalesced row -> F.normalize (eps 1e-12) -> bf16 hi / lo -> slab.
+__global__ void __launch_bounds__(256) dense_prep_kernel(const DaParams p) {
+  const DaGeo& g = p.g;
+  const int b = blockIdx.z, m = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 8 + warp;
+  if (q >= g.Spad || p.kept[b] == 0.f) return;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q < g.S) {
+    const float* map = (m == 0 ? p.G1 : p.G2) + ((long)b * g.HW + p.pix[(long)b * g.S + q]) * DA_C;
+    v = __ldg(reinterpret_cast<const float4*>(map) + lane);
   }
+  const float ss = warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+  const float inv = ss > 1e-24f ? rsqrtf(ss) : 1e12f;            // 1 / max(|x|, 1e-12)
+  uint32_t h01, l01, h23, l23;
+  split2(v.x * inv, v.y * inv, h01, l01);
+  split2(v.z * inv, v.w * inv, h23, l23);
+  uint8_t* slab = p.work + (((size_t)b * 2 + m) * g.nch + q / g.NC) * g.slab;
+  const uint32_t off = (uint32_t)(lane >> 1) * g.lbo + (uint32_t)(q % g.NC) * 16 + (uint32_t)(lane & 1) * 8;
+  *reinterpret_cast<uint2*>(slab + off) = make_uint2(h01, h23);
+  *reinterpret_cast<uint2*>(slab + g.half + off) = make_uint2(l01, l23);
 }
 
-__device__ __forceinline__ void da_store(const DaRows& R, int nrows, uint8_t* hi, uint8_t* lo, uint32_t lbo, int warp, int lane) {
+// three-product MMA over the 8 K=16 steps of the 128 channels: D (+)= A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (descriptor low words
+// advance by two 8-channel core-matrix columns per step; see umma_bf16_w)
+__device__ __forceinline__ void da_mma_xy(uint32_t d, uint32_t xs, uint32_t ys, const DaGeo& g, uint32_t idesc) {
+  const uint64_t xt = smem_desc(xs, g.lbo, 128), yt = smem_desc(ys, g.lbo, 128);
+  const uint32_t x_hi32 = (uint32_t)(xt >> 32), y_hi32 = (uint32_t)(yt >> 32);
+  const uint32_t lo16 = g.half >> 4, kk = (2u * g.lbo) >> 4;
+  uint32_t xa = (uint32_t)xt, ya = (uint32_t)yt;
+  umma_bf16_w(d, xa, x_hi32, ya, y_hi32, idesc, 0u);
+  umma_bf16_acc(d, xa + lo16, x_hi32, ya, y_hi32, idesc);
+  umma_bf16_acc(d, xa, x_hi32, ya + lo16, y_hi32, idesc);
 #pragma unroll
-  for (int u = 0; u < DA_U; ++u) {
-    const int r = warp * DA_U + u;
-    if (r >= nrows) break;
-    const float4 v = R.v[u];
-    const float ss = warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
-    const float inv = ss > 1e-24f ? rsqrtf(ss) : 1e12f;          // 1 / max(|x|, 1e-12)   (F.normalize)
-    uint32_t h01, l01, h23, l23;
-    split2(v.x * inv, v.y * inv, h01, l01);
-    split2(v.z * inv, v.w * inv, h23, l23);
-    const uint32_t off = (uint32_t)(lane >> 1) * lbo + (uint32_t)r * 16 + (uint32_t)(lane & 1) * 8;
-    *reinterpret_cast<uint2*>(hi + off) = make_uint2(h01, h23);
-    *reinterpret_cast<uint2*>(lo + off) = make_uint2(l01, l23);
+  for (int k = 1; k < DA_C / 16; ++k) {
+    xa += kk; ya += kk;
+    umma_bf16_acc(d, xa, x_hi32, ya, y_hi32, idesc);
+    umma_bf16_acc(d, xa + lo16, x_hi32, ya, y_hi32, idesc);
+    umma_bf16_acc(d, xa, x_hi32, ya + lo16, y_hi32, idesc);
   }
 }
 
@@ -135,10 +149,11 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = g.S;
-  const int row0 = strip * g.RS, row_end = min(S, row0 + g.RS);
-  // side 0: strip = rgb rows (G1), other = depth (G2); side 1: strip = depth rows, other = rgb
+  const int row0 = strip * g.NC, row_end = min(S, row0 + g.NC);
+  // side 0: strip = rgb rows (map 0), other = depth (map 1); side 1: strip = depth rows, other = rgb
   const float* Xmap = (side == 0 ? p.G1 : p.G2) + (long)b * g.HW * DA_C;
-  const float* Ymap = (side == 0 ? p.G2 : p.G1) + (long)b * g.HW * DA_C;
+  const uint8_t* Xslabs = p.work + ((size_t)b * 2 + side) * g.nch * g.slab;
+  const uint8_t* Yslabs = p.work + ((size_t)b * 2 + (1 - side)) * g.nch * g.slab;
   const long long* pix_b = p.pix + (long)b * S;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -149,19 +164,27 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
   float* s_zinv_o = s_lse_o + g.Spad;
   int* s_off = reinterpret_cast<int*>(s_zinv_o + g.Spad);
   float* s_red = reinterpret_cast<float*>(smem + g.off_red);
-  uint8_t* Xhi = smem + g.off_x;
-  uint8_t* Xlo = Xhi + 16 * g.lbo_x;
-  uint8_t* Yhi = smem + g.off_y;
-  uint8_t* Ylo = Yhi + 16 * g.lbo_y;
+  uint8_t* Xs = smem + g.off_x;
+  uint8_t* Ys = smem + g.off_y;                                  // forward: two slabs
   uint8_t* Ghi = smem + g.off_g;
-  uint8_t* Glo = Ghi + (uint32_t)(g.NC / 8) * g.lbo_x;
-  const uint32_t bar1 = smem_u32(bars), bar2 = bar1 + 8;
-  const uint32_t tmem_cols = BWD ? 256u : 128u;
+  uint8_t* Glo = Ghi + (uint32_t)(g.NC / 8) * g.lbo_g;
+  // barriers: 0 X slab, 1-2 Y slab buffers (TMA complete_tx), 3-4 affinity MMAs of accumulator 0 / 1, 5 gradient MMAs
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  const uint32_t tmem_cols = 256u;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar1, 1);
-    mbar_init(bar2, 1);
+    for (int i = 0; i < 6; ++i) mbar_init(BAR(i), 1);
     fence_mbar_init();
+    // operand slabs: the strip and the first chunk(s) of the other operand, one bulk copy each
+    mbar_expect_tx(BAR(0), g.slab);
+    tma_bulk_g2s(smem_u32(Xs), Xslabs + (size_t)strip * g.slab, g.slab, BAR(0));
+    mbar_expect_tx(BAR(1), g.slab);
+    tma_bulk_g2s(smem_u32(Ys), Yslabs, g.slab, BAR(1));
+    if (!BWD && g.nch > 1) {
+      mbar_expect_tx(BAR(2), g.slab);
+      tma_bulk_g2s(smem_u32(Ys + g.slab), Yslabs + g.slab, g.slab, BAR(2));
+    }
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_ptr), tmem_cols);
   for (int q = threadIdx.x; q < g.Spad; q += DA_THREADS) {
@@ -178,15 +201,8 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  DaRows R;                                                    // the slab in flight (X strip, then the Y chunks)
-  {
-    DaRows RX;
-    da_load(Xmap, s_off, row0, row_end, 128, RX, warp, lane);
-    da_load(Ymap, s_off, 0, S, g.NC, R, warp, lane);           // chunk 0 of the other operand: both gathers in flight together
-    da_store(RX, 128, Xhi, Xlo, g.lbo_x, warp, lane);
-  }
   const uint32_t tmem = *tmem_ptr;
-  const uint32_t tP = tmem, tdX = tmem + 128;
+  const uint32_t tdX = tmem + 128;                             // backward: gradient accumulator; forward: second affinity accumulator
 
   // this thread's strip row (TMEM lane) and column part (8-column groups part, part + DA_PARTS, ...)
   const int qtr = warp & 3, part = warp >> 2;
@@ -206,51 +222,56 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
   float mx = -INFINITY, se = 0.f, Z = 0.f, wl = 0.f;
   int am = 0;
   const uint32_t idesc1 = da_idesc(g.NC, 0), idesc2 = da_idesc(128, 1);
-  uint32_t ph1 = 0, ph2 = 0;
+  const uint32_t xs = smem_u32(Xs), ys = smem_u32(Ys);
 
-  for (int c = 0; c < g.nchunks; ++c) {
-    da_store(R, g.NC, Yhi, Ylo, g.lbo_y, warp, lane);
-    fence_proxy_async();
-    __syncthreads();
-    if (warp == 0) {
+  if (warp == 0) {                                             // affinity MMAs of chunk 0
+    mbar_wait(BAR(0), 0);
+    mbar_wait(BAR(1), 0);
+    tc_fence_after();
+    if (elect_one()) {
+      da_mma_xy(tmem, xs, ys, g, idesc1);
+      umma_commit(BAR(3));
+    }
+    __syncwarp();
+  }
+
+  for (int c = 0; c < g.nch; ++c) {
+    const int buf = BWD ? 0 : (c & 1);                         // Y buffer / accumulator of chunk c
+    const uint32_t tP = tmem + (uint32_t)(buf * 128);
+    if (!BWD && c + 1 < g.nch && warp == 0) {
+      // the MMAs of chunk c+1 run under the epilogue of chunk c (its accumulator was drained before the last __syncthreads)
+      const int nb = (c + 1) & 1;
+      mbar_wait(BAR(1 + nb), (uint32_t)(((c + 1) >> 1) & 1));
       tc_fence_after();
       if (elect_one()) {
-        // descriptor low words advance by one K=16 step (two 8-channel core-matrix columns) per iteration
-        const uint64_t xt = smem_desc(smem_u32(Xhi), g.lbo_x, 128), yt = smem_desc(smem_u32(Yhi), g.lbo_y, 128);
-        const uint32_t x_hi32 = (uint32_t)(xt >> 32), y_hi32 = (uint32_t)(yt >> 32);
-        const uint32_t xlo16 = (16u * g.lbo_x) >> 4, ylo16 = (16u * g.lbo_y) >> 4, xk = (2u * g.lbo_x) >> 4, yk = (2u * g.lbo_y) >> 4;
-        uint32_t xa = (uint32_t)xt, ya = (uint32_t)yt;
-        umma_bf16_w(tP, xa, x_hi32, ya, y_hi32, idesc1, 0u);
-        umma_bf16_acc(tP, xa + xlo16, x_hi32, ya, y_hi32, idesc1);
-        umma_bf16_acc(tP, xa, x_hi32, ya + ylo16, y_hi32, idesc1);
-#pragma unroll
-        for (int k = 1; k < DA_C / 16; ++k) {
-          xa += xk; ya += yk;
-          umma_bf16_acc(tP, xa, x_hi32, ya, y_hi32, idesc1);
-          umma_bf16_acc(tP, xa + xlo16, x_hi32, ya, y_hi32, idesc1);
-          umma_bf16_acc(tP, xa, x_hi32, ya + ylo16, y_hi32, idesc1);
-        }
-        umma_commit(bar1);
+        da_mma_xy(tmem + (uint32_t)(nb * 128), xs, ys + (uint32_t)nb * g.slab, g, idesc1);
+        umma_commit(BAR(3 + nb));
       }
       __syncwarp();
     }
-    if (c + 1 < g.nchunks) da_load(Ymap, s_off, (c + 1) * g.NC, S, g.NC, R, warp, lane);   // in flight during MMA + epilogue
-    mbar_wait(bar1, ph1);
-    ph1 ^= 1;
+    mbar_wait(BAR(3 + buf), (uint32_t)(BWD ? (c & 1) : ((c >> 1) & 1)));
     tc_fence_after();
+    if (!BWD && c + 2 < g.nch && threadIdx.x == 0) {           // Y buffer of chunk c is free: fetch chunk c+2 into it
+      mbar_expect_tx(BAR(1 + buf), g.slab);
+      tma_bulk_g2s(smem_u32(Ys + (size_t)buf * g.slab), Yslabs + (size_t)(c + 2) * g.slab, g.slab, BAR(1 + buf));
+    }
 
     // ---- epilogue over this thread's 8-column groups of the chunk
     for (int c0 = part * 8; c0 < g.NC; c0 += DA_PARTS * 8) {
       float v[8];
       tmem_ld8(tP + ((uint32_t)(qtr * 32) << 16) + (uint32_t)c0, v);
       const int q0 = c * g.NC + c0;
+      const float4 cya = *reinterpret_cast<const float4*>(s_cy + q0), cyb = *reinterpret_cast<const float4*>(s_cy + q0 + 4);
+      const float4 cxa = *reinterpret_cast<const float4*>(s_cx + q0), cxb = *reinterpret_cast<const float4*>(s_cx + q0 + 4);
+      const float cy[8] = {cya.x, cya.y, cya.z, cya.w, cyb.x, cyb.y, cyb.z, cyb.w};
+      const float cx[8] = {cxa.x, cxa.y, cxa.z, cxa.w, cxb.x, cxb.y, cxb.z, cxb.w};
       if (!BWD) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int q = q0 + i;
           const bool ok = q < S;
           const float l2 = v[i] * k2;
-          const float dy = s_cy[q] - my_y, dx = s_cx[q] - my_x;
+          const float dy = cy[i] - my_y, dx = cx[i] - my_x;
           const float w = ok ? ex2a(-DA_LOG2E * sqrta(fmaf(dy, dy, dx * dx))) : 0.f;
           Z += w;
           wl = fmaf(w, l2, wl);
@@ -259,18 +280,22 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
         }
       } else {
         float gv[8];
+        const float4 la = *reinterpret_cast<const float4*>(s_lse_o + q0), lb = *reinterpret_cast<const float4*>(s_lse_o + q0 + 4);
+        const float4 za = *reinterpret_cast<const float4*>(s_zinv_o + q0), zb = *reinterpret_cast<const float4*>(s_zinv_o + q0 + 4);
+        const float lo_[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+        const float zo_[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int q = q0 + i;
           const float l2 = v[i] * k2;
-          const float dy = s_cy[q] - my_y, dx = s_cx[q] - my_x;
+          const float dy = cy[i] - my_y, dx = cx[i] - my_x;
           const float w = ex2a(-DA_LOG2E * sqrta(fmaf(dy, dy, dx * dx)));
-          const float gg = coef * (ex2a(l2 - lse_own) - w * zinv_own) + coef_o * (ex2a(l2 - s_lse_o[q]) - w * s_zinv_o[q]);
+          const float gg = coef * (ex2a(l2 - lse_own) - w * zinv_own) + coef_o * (ex2a(l2 - lo_[i]) - w * zo_[i]);
           gv[i] = (q < S && row_ok) ? gg : 0.f;
         }
         uint4 gh, gl;
         split8(gv, gh, gl);
-        const uint32_t off = (uint32_t)(c0 >> 3) * g.lbo_x + (uint32_t)row * 16;
+        const uint32_t off = (uint32_t)(c0 >> 3) * g.lbo_g + (uint32_t)row * 16;
         *reinterpret_cast<uint4*>(Ghi + off) = gh;
         *reinterpret_cast<uint4*>(Glo + off) = gl;
       }
@@ -283,28 +308,42 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
       if (warp == 0) {
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t gh = smem_u32(Ghi), gl = smem_u32(Glo), yh = smem_u32(Yhi), yl = smem_u32(Ylo);
+          const uint32_t gh = smem_u32(Ghi), gl = smem_u32(Glo), yh = ys, yl = ys + g.half;
           // MN-major no-swizzle canonical layout ((1,n),(8,k)):((X,SBO),(1,LBO)) in 16-byte units: the 16-byte channel
-          // blocks are SBO = lbo_y apart, the 8-row K groups LBO = 128 bytes apart (roles swapped w.r.t. K-major; verified
+          // blocks are SBO = lbo apart, the 8-row K groups LBO = 128 bytes apart (roles swapped w.r.t. K-major; verified
           // on B200 against the fp32 statement)
-          const uint32_t b_lbo = 128u, b_sbo = g.lbo_y;
+          const uint32_t b_lbo = 128u, b_sbo = g.lbo;
 #pragma unroll 1
           for (int ks = 0; ks < g.NC / 16; ++ks) {
-            const uint64_t ah = smem_desc(gh + 2 * ks * g.lbo_x, g.lbo_x, 128), al = smem_desc(gl + 2 * ks * g.lbo_x, g.lbo_x, 128);
+            const uint64_t ah = smem_desc(gh + 2 * ks * g.lbo_g, g.lbo_g, 128), al = smem_desc(gl + 2 * ks * g.lbo_g, g.lbo_g, 128);
             const uint64_t bh = smem_desc(yh + ks * 256, b_lbo, b_sbo), bl = smem_desc(yl + ks * 256, b_lbo, b_sbo);
             umma_bf16(tdX, ah, bh, idesc2, (c > 0 || ks > 0) ? 1u : 0u);
             umma_bf16(tdX, al, bh, idesc2, 1u);
             umma_bf16(tdX, ah, bl, idesc2, 1u);
           }
-          umma_commit(bar2);
+          umma_commit(BAR(5));
         }
         __syncwarp();
       }
-      mbar_wait(bar2, ph2);
-      ph2 ^= 1;
+      mbar_wait(BAR(5), (uint32_t)(c & 1));
       tc_fence_after();
+      if (c + 1 < g.nch && warp == 0) {
+        // the Y slab and the G slab are free: fetch the next chunk and issue its affinity MMAs
+        if (lane == 0) {
+          mbar_expect_tx(BAR(1), g.slab);
+          tma_bulk_g2s(ys, Yslabs + (size_t)(c + 1) * g.slab, g.slab, BAR(1));
+        }
+        __syncwarp();
+        mbar_wait(BAR(1), (uint32_t)((c + 1) & 1));
+        tc_fence_after();
+        if (elect_one()) {
+          da_mma_xy(tmem, xs, ys, g, idesc1);
+          umma_commit(BAR(3));
+        }
+        __syncwarp();
+      }
     } else {
-      __syncthreads();         // every warp has drained P before the next chunk's MMAs overwrite it (and Y is restaged)
+      __syncthreads();         // every warp has drained this accumulator before the MMAs of chunk c+2 overwrite it
     }
   }
 
@@ -347,13 +386,13 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
     }
     s_red[(part * 128 + row) * 2 + 0] = dot;
     s_red[(part * 128 + row) * 2 + 1] = ss;
-    __syncthreads();                                  // also: all MMAs are complete, the X slabs are free
+    __syncthreads();                                  // also: all MMAs are complete, the X / Y slabs are free
     dot = 0.f; ss = 0.f;
 #pragma unroll
     for (int pp = 0; pp < DA_PARTS; ++pp) { dot += s_red[(pp * 128 + row) * 2]; ss += s_red[(pp * 128 + row) * 2 + 1]; }
     const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
     const float dotn = dot * inv;                     // <dXn, xn>
-    float* stage = reinterpret_cast<float*>(Xhi);     // [128][129] fp32
+    float* stage = reinterpret_cast<float*>(Xs);      // [128][129] fp32 (X slab + the head of the Y slab)
     for (int c0 = 0; c0 < CW; c0 += 8) {
       float v[8];
       tmem_ld8(tdX + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(part * CW + c0), v);
@@ -382,35 +421,56 @@ extern "C" {
 int hcm_dense_finish(const float* stat, const float* kept, const long long* use_depth, int B, int S, float* fin,
                      cudaStream_t stream);
 
-// stat [B][2][S][4] scratch (kept for the backward); fin[5] = loss_r2d, loss_d2r, acc_r2d, acc_d2r, B'
+// bytes of the operand-slab workspace of hcm_dense_affinity_fwd / _bwd
+long hcm_dense_affinity_work_bytes(int B, int S) {
+  DaGeo g = da_geo(S, 1, false);
+  return (long)B * 2 * g.nch * g.slab;
+}
+
+static int da_prep(const DaParams& p, int B, cudaStream_t stream) {
+  dim3 grid((p.g.Spad + 7) / 8, 2, B);
+  dense_prep_kernel<<<grid, 256, 0, stream>>>(p);
+  HCM_LAUNCH_CHECK("dense_affinity (operand slabs)");
+  return HCM_OK;
+}
+
+// stat [B][2][S][4] scratch (kept for the backward); fin[5] = loss_r2d, loss_d2r, acc_r2d, acc_d2r, B';
+// work: hcm_dense_affinity_work_bytes(B, S) bytes, 128-byte aligned (the normalised bf16 hi/lo operand slabs; the backward
+// re-uses them when called with prepared = 1 on the same G1, G2, pix)
 int hcm_dense_affinity_fwd(const float* G1, const float* G2, const long long* pix, const float* kept,
                            const long long* use_depth, int B, int S, int h, int dim, float inv_T, float* stat, float* fin,
-                           cudaStream_t stream) {
-  HCM_CHECK_ARG(G1 && G2 && pix && kept && stat && fin, "dense_affinity_fwd: null pointer");
+                           void* work, cudaStream_t stream) {
+  HCM_CHECK_ARG(G1 && G2 && pix && kept && stat && fin && work, "dense_affinity_fwd: null pointer");
   HCM_CHECK_ARG(dim == DA_C && B >= 1 && S >= 1 && h >= 1, "dense_affinity_fwd: bad args (dim=%d B=%d S=%d h=%d)", dim, B, S, h);
+  HCM_CHECK_ARG(((size_t)work & 127) == 0, "dense_affinity_fwd: workspace must be 128-byte aligned");
   DaParams p = {};
-  p.G1 = G1; p.G2 = G2; p.pix = pix; p.kept = kept; p.stat = stat; p.inv_T = inv_T;
+  p.G1 = G1; p.G2 = G2; p.pix = pix; p.kept = kept; p.stat = stat; p.inv_T = inv_T; p.work = reinterpret_cast<uint8_t*>(work);
   p.g = da_geo(S, h, false);
+  HCM_CHECK_ARG(p.g.smem_bytes <= 227 * 1024, "dense_affinity_fwd: shared memory (%u bytes)", p.g.smem_bytes);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(dense_affinity_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(dense_affinity_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
-  dim3 grid(p.g.nstrips, 2, B);
+  int rc = da_prep(p, B, stream);
+  if (rc != HCM_OK) return rc;
+  dim3 grid(p.g.nch, 2, B);
   dense_affinity_kernel<false><<<grid, DA_THREADS, p.g.smem_bytes, stream>>>(p);
   HCM_LAUNCH_CHECK("dense_affinity_fwd");
   return hcm_dense_finish(stat, kept, use_depth, B, S, fin, stream);
 }
 
-// dG1, dG2 [B][h*h][128] are ACCUMULATED into (atomics: sampled pixels repeat); the caller zeroes them
+// dG1, dG2 [B][h*h][128] are ACCUMULATED into (atomics: sampled pixels repeat); the caller zeroes them.
+// prepared = 1: `work` still holds the slabs written by hcm_dense_affinity_fwd for the same G1, G2, pix; 0: they are rebuilt.
 int hcm_dense_affinity_bwd(const float* G1, const float* G2, const long long* pix, const float* stat, const float* kept,
                            const float* fin, int B, int S, int h, int dim, float inv_T, float gscale_r2d, float gscale_d2r, float* dG1,
-                           float* dG2, cudaStream_t stream) {
-  HCM_CHECK_ARG(G1 && G2 && pix && stat && kept && fin && dG1 && dG2, "dense_affinity_bwd: null pointer");
+                           float* dG2, void* work, int prepared, cudaStream_t stream) {
+  HCM_CHECK_ARG(G1 && G2 && pix && stat && kept && fin && dG1 && dG2 && work, "dense_affinity_bwd: null pointer");
   HCM_CHECK_ARG(dim == DA_C && B >= 1 && S >= 1 && h >= 1, "dense_affinity_bwd: bad args (dim=%d B=%d S=%d h=%d)", dim, B, S, h);
+  HCM_CHECK_ARG(((size_t)work & 127) == 0, "dense_affinity_bwd: workspace must be 128-byte aligned");
   DaParams p = {};
   p.G1 = G1; p.G2 = G2; p.pix = pix; p.kept = kept; p.fin = fin; p.stat = const_cast<float*>(stat);
-  p.dG1 = dG1; p.dG2 = dG2; p.inv_T = inv_T; p.gscale = gscale_r2d; p.gscale_o = gscale_d2r;
+  p.dG1 = dG1; p.dG2 = dG2; p.inv_T = inv_T; p.gscale = gscale_r2d; p.gscale_o = gscale_d2r; p.work = reinterpret_cast<uint8_t*>(work);
   p.g = da_geo(S, h, true);
   HCM_CHECK_ARG(p.g.smem_bytes <= 227 * 1024, "dense_affinity_bwd: shared memory (%u bytes)", p.g.smem_bytes);
   static bool attr = false;
@@ -418,7 +478,11 @@ int hcm_dense_affinity_bwd(const float* G1, const float* G2, const long long* pi
     cudaFuncSetAttribute(dense_affinity_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
-  dim3 grid(p.g.nstrips, 2, B);
+  if (!prepared) {
+    int rc = da_prep(p, B, stream);
+    if (rc != HCM_OK) return rc;
+  }
+  dim3 grid(p.g.nch, 2, B);
   dense_affinity_kernel<true><<<grid, DA_THREADS, p.g.smem_bytes, stream>>>(p);
   HCM_LAUNCH_CHECK("dense_affinity_bwd");
   return HCM_OK;

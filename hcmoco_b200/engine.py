@@ -887,7 +887,8 @@ class Engine:
         p.f(K.dense_kept, self.depth_mask, B, self.R, h, kept)
         # one fused kernel: gather + L2-norm + S x S x 128 affinity (tcgen05) + soft-target statistics; L[b][i][j] = <d_i, a_j>/T
         # stays on chip (the unfused chain gather_l2norm -> gemm -> dense_stats remains in the C-ABI and the kernel tests)
-        p.f(K.dense_affinity_fwd, G1.data, G2.data, self.dense_idx, kept, self.use_depth, B, S, h, 128, 1.0 / T, stat, fin_d)
+        dwork = K.empty((K.dense_affinity_work_bytes(B, S) + 3) // 4)     # normalised bf16 hi/lo operand slabs (forward -> backward)
+        p.f(K.dense_affinity_fwd, G1.data, G2.data, self.dense_idx, kept, self.use_depth, B, S, h, 128, 1.0 / T, stat, fin_d, dwork)
         p.f(K.bn_apply, fin_d, None, None, None, None, None, 0, self.losses[6:8], 1, 2)
         p.f(K.bn_apply, fin_d[2:4], None, None, None, None, None, 0, self.accs[6:8], 1, 2)
         # --- joints: F rows [0,BJ) rgb pixels, [BJ,2BJ) depth pixels (also the SCL feature matrix)
@@ -937,7 +938,7 @@ class Engine:
             gs, acc = self._slot_grad(self.feat3_slot, (B, J, 128))
             p.b(K.gather_l2norm_bwd, dSk, 128, Sk, 128, inv_s, None, 0, 1, B * J, 128, gs, 128, acc)
             # dense: affinity recomputed on chip, logit gradient -> second MMA -> L2-norm backward -> atomic scatter
-            p.b(K.dense_affinity_bwd, G1.data, G2.data, self.dense_idx, stat, kept, fin_d, B, S, h, 128, iT, 1.0, 1.0, g1, g2)
+            p.b(K.dense_affinity_bwd, G1.data, G2.data, self.dense_idx, stat, kept, fin_d, B, S, h, 128, iT, 1.0, 1.0, g1, g2, dwork, 1)
 
         p.on_backward(backward)
 

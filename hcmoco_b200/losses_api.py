@@ -32,17 +32,18 @@ class _DenseFn(torch.autograd.Function):
         kept = K.empty(B)
         K.dense_kept(mask, B, mask.shape[-1], h, kept)
         stat, fin = K.zeros(B, 2, S, 4), K.zeros(8)
-        K.dense_affinity_fwd(G1, G2, idx, kept, ud, B, S, h, 128, 1.0 / T, stat, fin)
+        work = K.empty((K.dense_affinity_work_bytes(B, S) + 3) // 4)
+        K.dense_affinity_fwd(G1, G2, idx, kept, ud, B, S, h, 128, 1.0 / T, stat, fin, work)
         ctx.K, ctx.T, ctx.dims = K, T, (B, S, h)
-        ctx.save_for_backward(G1, G2, idx, stat, kept, fin)
+        ctx.save_for_backward(G1, G2, idx, stat, kept, fin, work)
         return fin[0].clone(), fin[1].clone(), fin[2].clone(), fin[3].clone()
 
     @staticmethod
     def backward(ctx, g0, g1, _a0, _a1):
         K, (B, S, h) = ctx.K, ctx.dims
-        G1, G2, idx, stat, kept, fin = ctx.saved_tensors
+        G1, G2, idx, stat, kept, fin, work = ctx.saved_tensors
         d1, d2 = torch.zeros_like(G1), torch.zeros_like(G2)
-        K.dense_affinity_bwd(G1, G2, idx, stat, kept, fin, B, S, h, 128, 1.0 / ctx.T, _gscale(g0), _gscale(g1), d1, d2)
+        K.dense_affinity_bwd(G1, G2, idx, stat, kept, fin, B, S, h, 128, 1.0 / ctx.T, _gscale(g0), _gscale(g1), d1, d2, work, 1)
         return None, d1.permute(0, 3, 1, 2), d2.permute(0, 3, 1, 2), None, None, None, None
 
 

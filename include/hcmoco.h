@@ -163,13 +163,16 @@ int hcm_dense_finish(const float* stat, const float* kept, const long long* use_
    :695-699), soft-target log-softmax statistics (:702-721) in the epilogue.  Nothing S x S is written to memory.
    stat [B][2][S][4] is scratch kept for the backward; fin[5] = loss_r2d, loss_d2r, acc_r2d, acc_d2r, B'.
    The backward recomputes the affinity and ACCUMULATES into dG1, dG2 (atomics; the caller zeroes them);
-   gscale_r2d / gscale_d2r = d(total)/d(loss_r2d), d(total)/d(loss_d2r) (1, 1 for the reference's plain sum, :980). */
+   gscale_r2d / gscale_d2r = d(total)/d(loss_r2d), d(total)/d(loss_d2r) (1, 1 for the reference's plain sum, :980).
+   A first kernel gathers, L2-normalises and splits the S sampled pixels of both maps ONCE per sample into bf16 hi/lo operand
+   slabs in `work`; the main kernel streams them with cp.async.bulk (TMA).  prepared = 1: `work` still holds the forward's slabs. */
+long hcm_dense_affinity_work_bytes(int B, int S);   /* operand-slab workspace (128-byte aligned, caller-owned) */
 int hcm_dense_affinity_fwd(const float* G1, const float* G2, const long long* pix, const float* kept,
                            const long long* use_depth, int B, int S, int h, int dim, float inv_T, float* stat, float* fin,
-                           cudaStream_t stream);
+                           void* work, cudaStream_t stream);
 int hcm_dense_affinity_bwd(const float* G1, const float* G2, const long long* pix, const float* stat, const float* kept,
                            const float* fin, int B, int S, int h, int dim, float inv_T, float gscale_r2d, float gscale_d2r,
-                           float* dG1, float* dG2, cudaStream_t stream);
+                           float* dG1, float* dG2, void* work, int prepared, cudaStream_t stream);
 int hcm_joint_stats(const float* Lr, const float* Ld, const int* joints_vis, const long long* use_depth, int B, int J,
                     float* rs, float* lse, float* fin, cudaStream_t stream);
 int hcm_joint_grad(float* Lr, float* Ld, const int* joints_vis, const long long* use_depth, const float* lse,

@@ -27,10 +27,11 @@ for (B, h, S) in ((4, 16, 60), (3, 32, 400), (32, 64, 400), (2, 8, 130)):
     kept[0] = 1
     use_depth = torch.ones(B, dtype=torch.int64).cuda()
     T = 0.07
+    work = torch.empty((K.dense_affinity_work_bytes(B, S) + 3) // 4, device="cuda")
     out = {}
     for name, kk in (("cuda", K), ("ref", R)):
         stat, fin = torch.zeros(B, 2, S, 4).cuda(), torch.zeros(8).cuda()
-        kk.dense_affinity_fwd(G1, G2, pix, kept, use_depth, B, S, h, 128, 1.0 / T, stat, fin)
+        kk.dense_affinity_fwd(G1, G2, pix, kept, use_depth, B, S, h, 128, 1.0 / T, stat, fin, work)
         out[name] = (stat, fin)
     torch.cuda.synchronize()
     m = kept != 0
@@ -41,9 +42,9 @@ for (B, h, S) in ((4, 16, 60), (3, 32, 400), (32, 64, 400), (2, 8, 130)):
         out["ref"][1][:2].tolist()), flush=True)
     stat, fin = out["ref"]
     d1r, d2r = torch.zeros_like(G1), torch.zeros_like(G2)
-    R.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1.0 / T, 1.0, 1.0, d1r, d2r)
+    R.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1.0 / T, 1.0, 1.0, d1r, d2r, work, 0)
     d1, d2 = torch.zeros_like(G1), torch.zeros_like(G2)
-    K.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1.0 / T, 1.0, 1.0, d1, d2)
+    K.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1.0 / T, 1.0, 1.0, d1, d2, work, 0)
     torch.cuda.synchronize()
     print("   bwd: dG1 %.2e dG2 %.2e" % (rel(d1, d1r), rel(d2, d2r)), flush=True)
     if B == 32:
@@ -53,10 +54,10 @@ for (B, h, S) in ((4, 16, 60), (3, 32, 400), (32, 64, 400), (2, 8, 130)):
         for it in range(2):
             ev[0].record()
             for i in range(20):
-                K.dense_affinity_fwd(G1, G2, pix, kept, use_depth, B, S, h, 128, 1.0 / T, stat, fin)
+                K.dense_affinity_fwd(G1, G2, pix, kept, use_depth, B, S, h, 128, 1.0 / T, stat, fin, work)
             ev[1].record()
             for i in range(20):
-                K.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1.0 / T, 1.0, 1.0, d1, d2)
+                K.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, 1.0 / T, 1.0, 1.0, d1, d2, work, 0)
             ev[2].record()
             torch.cuda.synchronize()
         nk = int(kept.sum())

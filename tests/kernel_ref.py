@@ -478,7 +478,10 @@ class TorchKernels:
         return 0
 
     # fused form (dense_affinity.cu) = gather_l2norm x2 -> affinity GEMM -> dense_stats / dense_grad -> GEMMs -> scatter
-    def dense_affinity_fwd(self, G1, G2, pix, kept, use_depth, B, S, h, dim, inv_T, stat, fin):
+    def dense_affinity_work_bytes(self, B, S):
+        return 16
+
+    def dense_affinity_fwd(self, G1, G2, pix, kept, use_depth, B, S, h, dim, inv_T, stat, fin, work=None):
         HW = h * h
         A, D = torch.empty(B * S, dim, dtype=G1.dtype, device=G1.device), torch.empty(B * S, dim, dtype=G1.dtype, device=G1.device)
         self.gather_l2norm(G1, 0, pix, HW, S, B * S, dim, A, dim, None)
@@ -491,7 +494,8 @@ class TorchKernels:
         sv[k != 0] = st[k != 0]          # the fused kernel skips dropped samples
         return 0
 
-    def dense_affinity_bwd(self, G1, G2, pix, stat, kept, fin, B, S, h, dim, inv_T, gscale_r2d, gscale_d2r, dG1, dG2):
+    def dense_affinity_bwd(self, G1, G2, pix, stat, kept, fin, B, S, h, dim, inv_T, gscale_r2d, gscale_d2r, dG1, dG2, work=None,
+                           prepared=0):
         HW = h * h
         mk = lambda *s: torch.empty(*s, dtype=G1.dtype, device=G1.device)      # noqa: E731
         A, D, ia, idn = mk(B * S, dim), mk(B * S, dim), mk(B * S), mk(B * S)

@@ -62,7 +62,8 @@ def test_argument_errors_are_reported_not_fatal(lib):
     # argument checks run before anything touches the device: negative code + message, process stays alive
     assert lib.hcm_gather_l2norm(None, 0, None, 0, 1, 4, 128, None, 128, None, None) < 0
     assert b"gather_l2norm" in lib.hcm_last_error()
-    assert lib.hcm_dense_affinity_fwd(None, None, None, None, None, 2, 400, 64, 128, ctypes.c_float(14.0), None, None, None) < 0
+    assert lib.hcm_dense_affinity_fwd(None, None, None, None, None, 2, 400, 64, 128, ctypes.c_float(14.0), None, None, None, None) < 0
+    assert lib.hcm_dense_affinity_work_bytes(32, 400) == 32 * 2 * 4 * 2 * 16 * (112 * 16 + 16)
     assert b"dense_affinity_fwd" in lib.hcm_last_error()
     assert lib.hcm_tc_conv(None, None, None, None, 2, 16, 16, 18, 18, 3, 1, None, None, 0, 0, None) < 0
     assert b"tc_conv" in lib.hcm_last_error()

@@ -289,9 +289,10 @@ def test_dense_affinity_fused(KK, B, h, S, gs):
     use_depth = torch.ones(B, dtype=torch.int64, device=DEV)
     iT = 1.0 / 0.07
     out = []
+    work = torch.empty((kc.dense_affinity_work_bytes(B, S) + 3) // 4, device=DEV)
     for kk in (kc, kr):
         stat, fin = torch.zeros(B, 2, S, 4, device=DEV), torch.zeros(8, device=DEV)
-        kk.dense_affinity_fwd(G1, G2, pix, kept, use_depth, B, S, h, 128, iT, stat, fin)
+        kk.dense_affinity_fwd(G1, G2, pix, kept, use_depth, B, S, h, 128, iT, stat, fin, work)
         out.append((stat, fin))
     torch.cuda.synchronize()
     m = kept != 0
@@ -303,16 +304,16 @@ def test_dense_affinity_fused(KK, B, h, S, gs):
     d = []
     for kk in (kc, kr):
         d1, d2 = torch.zeros_like(G1), torch.zeros_like(G2)
-        kk.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, iT, gs[0], gs[1], d1, d2)
+        kk.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, iT, gs[0], gs[1], d1, d2, work, int(kk is kc and S != 130))
         d.append((d1, d2))
     torch.cuda.synchronize()
     assert rel(d[0][0], d[1][0]) < 2e-4 and rel(d[0][1], d[1][1]) < 2e-4
     # all depth off -> exact zeros, and a backward that adds nothing
     stat, fin = torch.zeros(B, 2, S, 4, device=DEV), torch.ones(8, device=DEV)
-    kc.dense_affinity_fwd(G1, G2, pix, kept, torch.zeros_like(use_depth), B, S, h, 128, iT, stat, fin)
+    kc.dense_affinity_fwd(G1, G2, pix, kept, torch.zeros_like(use_depth), B, S, h, 128, iT, stat, fin, work)
     assert float(fin[:5].abs().sum()) == 0.0
     d1, d2 = torch.zeros_like(G1), torch.zeros_like(G2)
-    kc.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, iT, gs[0], gs[1], d1, d2)
+    kc.dense_affinity_bwd(G1, G2, pix, stat, kept, fin, B, S, h, 128, iT, gs[0], gs[1], d1, d2, work, 0)
     assert float(d1.abs().sum() + d2.abs().sum()) == 0.0
 
 
