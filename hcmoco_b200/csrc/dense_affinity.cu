@@ -81,6 +81,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, float (&v)[8]) {      // values valid after tmem_ld_wait()
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "r"(taddr));
+}
+
 // The epilogue is INSTRUCTION-bound (ncu, round 2: 30 M warp instructions per launch, 115 per 32 logits; the accurate sqrtf and
 // the branchy online softmax were most of it), so it works in log2 units with the approximate MUFU forms (2^-22 relative):
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -188,10 +194,11 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_ptr), tmem_cols);
   for (int q = threadIdx.x; q < g.Spad; q += DA_THREADS) {
-    const long long px = q < S ? pix_b[q] : 0;
-    s_cy[q] = (float)(px / g.h);
-    s_cx[q] = (float)(px % g.h);
-    s_off[q] = (int)px * DA_C;
+    const int px = q < S ? (int)pix_b[q] : 0;
+    const int py = px / g.h;
+    s_cy[q] = (float)py;
+    s_cx[q] = (float)(px - py * g.h);
+    s_off[q] = px * DA_C;
     if (BWD) {
       const float* so = p.stat + (((long)b * 2 + (1 - side)) * S + (q < S ? q : 0)) * 4;
       s_lse_o[q] = so[0] * DA_LOG2E;                       // log2 units (see the epilogue)
@@ -256,10 +263,10 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
       tma_bulk_g2s(smem_u32(Ys + (size_t)buf * g.slab), Yslabs + (size_t)(c + 2) * g.slab, g.slab, BAR(1 + buf));
     }
 
-    // ---- epilogue over this thread's 8-column groups of the chunk
-    for (int c0 = part * 8; c0 < g.NC; c0 += DA_PARTS * 8) {
-      float v[8];
-      tmem_ld8(tP + ((uint32_t)(qtr * 32) << 16) + (uint32_t)c0, v);
+    // ---- epilogue over this thread's 8-column groups of the chunk, TWO groups per iteration: the work of a group is one
+    // dependent chain per logit (TMEM load -> MUFU sqrt -> MUFU ex2 -> ...; ncu: short-scoreboard + fixed-latency stalls dominate
+    // with 4 warps per scheduler), so two groups in flight double the independent instructions the scheduler can pick from
+    auto group = [&](const float (&v)[8], int c0) {
       const int q0 = c * g.NC + c0;
       const float4 cya = *reinterpret_cast<const float4*>(s_cy + q0), cyb = *reinterpret_cast<const float4*>(s_cy + q0 + 4);
       const float4 cxa = *reinterpret_cast<const float4*>(s_cx + q0), cxb = *reinterpret_cast<const float4*>(s_cx + q0 + 4);
@@ -298,6 +305,21 @@ __global__ void __launch_bounds__(DA_THREADS, 1) dense_affinity_kernel(const DaP
         const uint32_t off = (uint32_t)(c0 >> 3) * g.lbo_g + (uint32_t)row * 16;
         *reinterpret_cast<uint4*>(Ghi + off) = gh;
         *reinterpret_cast<uint4*>(Glo + off) = gl;
+      }
+    };
+    const uint32_t trow = tP + ((uint32_t)(qtr * 32) << 16);
+    for (int c0 = part * 8; c0 < g.NC; c0 += 2 * DA_PARTS * 8) {
+      const int c1 = c0 + DA_PARTS * 8;
+      float va[8], vb[8];
+      if (c1 < g.NC) {
+        tmem_ld8_issue(trow + (uint32_t)c0, va);
+        tmem_ld8_issue(trow + (uint32_t)c1, vb);
+        tmem_ld_wait();
+        group(va, c0);
+        group(vb, c1);
+      } else {
+        tmem_ld8(trow + (uint32_t)c0, va);
+        group(va, c0);
       }
     }
     tc_fence_before();
