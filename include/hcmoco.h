@@ -194,6 +194,13 @@ int hcm_sgcn_aggregate_bwd(const float* dxa, const float* x, const float* A, int
                            int accumulate, float* dA, cudaStream_t stream);
 int hcm_joint_mean(const float* x, int B, int J, int C, float* out, cudaStream_t stream);
 int hcm_joint_mean_bwd(const float* dout, int B, int J, int C, float* dx, int accumulate, cudaStream_t stream);
+/* ---- input staging for real data (stage_input.cu): datasets/dataset.py:104-160 (resized crop of the decoded RGB / depth frame,
+ *      flip, /255 + ImageNet mean/std, mm -> m) and :594-602 (depth_mask = depth > 0, depth -= its mean over the mask).
+ *      rgb [B,Hs,Ws,3] uint8, depth [B,Hs,Ws] uint16 (mm), crop [B,4] = (top, left, height, width), flip [B] (may be null),
+ *      has_depth [B] (null = all) -> x [B,6,R,R] fp32, depth_mask [B,R,R]; sums [B,2] uint64 scratch (exact mm sum / count). ---- */
+int hcm_stage_input(const unsigned char* rgb, const unsigned short* depth, const int* crop, const int* flip,
+                    const long long* has_depth, int B, int Hs, int Ws, int R, unsigned long long* sums, float* x,
+                    float* depth_mask, cudaStream_t stream);
 int hcm_sgd_step(float* p, const float* g, float* buf, long n, float lr, float momentum, float wd, int first,
                  float gscale, cudaStream_t stream);
 int hcm_zero(void* p, long bytes, cudaStream_t stream);

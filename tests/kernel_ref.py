@@ -519,6 +519,50 @@ class TorchKernels:
         self.gather_l2norm_bwd(dD.contiguous(), dim, D, dim, idn, pix, HW, S, B * S, dim, dG2, 0, 1)
         return 0
 
+    # ---- input staging (stage_input.cu): integer indexing / mask / mm sums exact, fp32 bilinear for the RGB planes
+    def stage_input(self, rgb, depth, crop, flip, has_depth, B, Hs, Ws, R, sums, x, mask):
+        dev = rgb.device
+        yy = torch.arange(R, device=dev)
+        mean_c = torch.tensor([0.485, 0.456, 0.406], device=dev, dtype=torch.float32)
+        std_c = torch.tensor([0.229, 0.224, 0.225], device=dev, dtype=torch.float32)
+        for b in range(B):
+            i, j, h, w = [int(v) for v in crop[b]]
+            fl = flip is not None and int(flip[b]) != 0
+            hd = has_depth is None or int(has_depth[b]) != 0
+            xs = (R - 1 - yy) if fl else yy                                   # source column of each output column
+            # nearest source pixel (exact integer arithmetic)
+            sy = i + torch.clamp(((2 * yy + 1) * h) // (2 * R), max=h - 1)
+            sx = j + torch.clamp(((2 * xs + 1) * w) // (2 * R), max=w - 1)
+            oky, okx = (sy >= 0) & (sy < Hs), (sx >= 0) & (sx < Ws)
+            d = depth[b].to(torch.int64)[sy.clamp(0, Hs - 1)][:, sx.clamp(0, Ws - 1)]
+            d = d * (oky.view(-1, 1) & okx.view(1, -1))
+            sums[b, 0], sums[b, 1] = int(d.sum()), int((d > 0).sum())         # (sums are flip-invariant)
+            cnt = int(sums[b, 1])
+            mean = torch.tensor(float(int(sums[b, 0])) / cnt / 1000.0 if cnt else 0.0, dtype=torch.float64).to(torch.float32)
+            if not hd:
+                d = torch.zeros_like(d)
+            m = d > 0
+            dn = torch.where(m, d.to(torch.float32) / 1000.0 - mean, torch.zeros((), device=dev))
+            x[b, 3], x[b, 4], x[b, 5] = dn, dn, dn
+            mask[b] = m.to(mask.dtype)
+            # bilinear RGB, fp32, the same operation order as the kernel
+            f32 = torch.float32
+            fy = torch.clamp((yy.to(f32) + 0.5) * (torch.tensor(h, dtype=f32) / torch.tensor(R, dtype=f32)) - 0.5, 0.0, float(h - 1))
+            fx = torch.clamp((xs.to(f32) + 0.5) * (torch.tensor(w, dtype=f32) / torch.tensor(R, dtype=f32)) - 0.5, 0.0, float(w - 1))
+            y0, x0 = fy.to(torch.int64), fx.to(torch.int64)
+            y1, x1 = torch.clamp(y0 + 1, max=h - 1), torch.clamp(x0 + 1, max=w - 1)
+            wy, wx = fy - y0.to(f32), fx - x0.to(f32)
+            img = rgb[b].to(f32)
+            acc = torch.zeros(R, R, 3, device=dev, dtype=f32)
+            for t in range(4):
+                ys, xs_ = i + (y1 if t & 2 else y0), j + (x1 if t & 1 else x0)
+                wt = ((wy if t & 2 else 1.0 - wy).view(-1, 1) * (wx if t & 1 else 1.0 - wx).view(1, -1)).to(f32)
+                ok = ((ys >= 0) & (ys < Hs)).view(-1, 1) & ((xs_ >= 0) & (xs_ < Ws)).view(1, -1)
+                px = img[ys.clamp(0, Hs - 1)][:, xs_.clamp(0, Ws - 1)]
+                acc = torch.where(ok.unsqueeze(-1), torch.addcmul(acc, wt.unsqueeze(-1), px), acc)
+            x[b, 0:3] = ((acc / 255.0 - mean_c) / std_c).permute(2, 0, 1).to(x.dtype)
+        return 0
+
     def joint_stats(self, Lr, Ld, vis, use_depth, B, J, rs, lse, fin):
         r = rs.reshape(B, 2, 3)
         ls = lse.reshape(B, 2, J)

@@ -514,3 +514,42 @@ def test_tc_wgrad_stride2(KK, shape):
     kc.tc_wgrad(x, dy, dw1, 0, B, H, W, Cin, Cout, 3, 2, sc, sh, 1)
     kr.conv2d_wgrad(x, dy, dw2, B, H, W, Cin, Cout, 3, 2, sc, sh, 1)
     assert rel(dw1, dw2) < 3e-5, rel(dw1, dw2)
+
+
+@pytest.mark.parametrize("R,Hs,Ws", [(256, 424, 512), (64, 100, 80)])
+def test_stage_input(KK, R, Hs, Ws):
+    """GPU input staging (datasets/dataset.py:104-160, 594-602) against its torch restatement: nearest-neighbour depth, mask and the
+    millimetre sum / pixel count are bit-exact (integer work); the bilinear RGB planes and the mean-centred depth within fp32 rounding."""
+    kc, kr = KK
+    B = 5
+    g = torch.Generator().manual_seed(R)
+    rgb = torch.randint(0, 256, (B, Hs, Ws, 3), generator=g, dtype=torch.uint8).to(DEV)
+    dmm = torch.randint(500, 4000, (B, Hs, Ws), generator=g, dtype=torch.int32)
+    yy, xx = torch.meshgrid(torch.arange(Hs), torch.arange(Ws), indexing="ij")
+    body = (((yy - Hs / 2) / (0.4 * Hs)) ** 2 + ((xx - Ws / 2) / (0.25 * Ws)) ** 2) <= 1.0
+    dmm = (dmm * body).to(torch.uint16)
+    dmm[3] = 0                                                     # an empty depth frame: count 0, mean 0, mask 0
+    depth = dmm.to(DEV)
+    # crop windows: inside the frame, partly outside (negative corner / past the border), whole frame
+    crop = torch.tensor([[10, 20, Hs - 40, Ws - 60], [-15, -7, Hs // 2, Ws // 2], [Hs // 3, Ws // 3, Hs, Ws], [0, 0, Hs, Ws],
+                         [5, 5, 37, 53]], dtype=torch.int32).to(DEV)
+    flip = torch.tensor([0, 1, 0, 1, 1], dtype=torch.int32).to(DEV)
+    has_depth = torch.tensor([1, 1, 1, 1, 0], dtype=torch.int64).to(DEV)
+    outs = []
+    for kk in (kc, kr):
+        sums = torch.zeros(B, 2, dtype=torch.int64, device=DEV)
+        x = torch.full((B, 6, R, R), float("nan"), device=DEV)
+        mask = torch.full((B, R, R), float("nan"), device=DEV)
+        kk.stage_input(rgb, depth, crop, flip, has_depth, B, Hs, Ws, R, sums, x, mask)
+        outs.append((sums, x, mask))
+    torch.cuda.synchronize()
+    (s0, x0, m0), (s1, x1, m1) = outs
+    assert torch.equal(s0, s1) and int(s1[0, 1]) > 0 and int(s1[3, 1]) == 0          # exact integer sums / counts
+    assert torch.equal(m0, m1) and float(m1[4].sum()) == 0.0                         # mask exact; no depth -> empty mask
+    assert torch.equal((x0[:, 3] != 0), (x1[:, 3] != 0))
+    assert float((x0[:, 3:] - x1[:, 3:]).abs().max()) < 1e-6                         # same mm values, mean within fp32 rounding
+    assert torch.equal(x0[:, 3], x0[:, 4]) and torch.equal(x0[:, 3], x0[:, 5])
+    assert float((x0[:, :3] - x1[:, :3]).abs().max()) < 2e-5 and torch.isfinite(x0).all()
+    # mean-centring: the masked depth of every depth-bearing sample sums to ~0
+    for b in range(3):
+        assert abs(float(x0[b, 3].double().sum())) / max(1.0, float(s1[b, 1])) < 1e-6
