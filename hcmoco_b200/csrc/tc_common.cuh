@@ -8,6 +8,22 @@ namespace {
 
 __host__ __device__ inline int ceil_to(int a, int b) { return (a + b - 1) / b * b; }
 
+// Division of 0 <= n < 2^31 by a launch constant without the ~40-instruction emulated integer divide (the position decode of
+// every staged row and, worse, the per-tile bookkeeping of the single MMA-issuing warp): m = ceil(2^(31+l) / d), l = ceil(log2 d),
+// n / d = umulhi(n, m) >> (l - 1)  (error term n / 2^(31+l) < 2^-l <= 1/d, so the floor is exact).
+struct FastDiv { uint32_t d, m, s; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f; f.d = d; f.m = 0; f.s = 0;
+  if (d <= 1) return f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  const unsigned long long k = 31 + l, p2 = 1ull << k;
+  f.m = (uint32_t)((p2 + d - 1) / d);
+  f.s = l - 1;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return f.d <= 1 ? n : (__umulhi(n, f.m) >> f.s); }
+
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -149,74 +165,138 @@ __device__ __forceinline__ uint32_t swz16(uint32_t row, uint32_t kb, uint32_t SW
 // call (channel offset, destination column and the 8+8 BN coefficients live in registers) and walks the rows, two rows
 // (up to 8 loads) in flight: ~9 instructions per channel instead of the ~57 of a (row, 2-4 channel) unit with per-unit
 // table lookups.  Consecutive lanes read consecutive chunks of a row, then the next row: fully coalesced.
+// The kernels are instruction-issue-bound in these warps (ncu, 64x64 18->18: ~8.6k warp instructions per 128-position tile,
+// 67 % of the issue slots), so the FULL chunks run a path without per-channel validity predicates, and the partial tail chunk
+// of a row (18 channels = 2 full chunks + 2 channels, 36 = 4 + 4) is a separate cheap pass that loads, splits and stores only
+// its valid channels: the rest of its 16 bytes keeps the zeros written at kernel start (or finite stale values that meet zero
+// weights / never-read accumulator columns).  Before, a tail chunk cost as much as a full one: 33 % of the items of an 18-channel row.
 // V = 4: 16-byte loads (C % 4 == 0), V = 2: 8-byte loads (C even).  Threads t in [0, TS) of one team call it together.
 template <int V>
 __device__ __forceinline__ void stage_rows8(const float* __restrict__ src, int C, int c_first, int nch, int rows,
                                             const int* __restrict__ src_tab, int tab_stride, int tab_off, uint8_t* hi_base,
                                             uint32_t lo_off, uint32_t plane, uint32_t SW, uint32_t byte0, const float* s_sc,
                                             const float* s_sh, bool affine, int relu, int t, int TS) {
-  const int cpp = (nch + 7) >> 3;                       // chunks per row
-  const int dpos = TS / cpp;                            // rows advanced per step (TS >= 128 >= cpp)
-  if (t >= dpos * cpp) return;
-  const int pos0 = t / cpp, ch = t - pos0 * cpp;
-  const int c = c_first + ch * 8;
-  const int nval = min(8, nch - ch * 8);
-  const uint32_t kb = byte0 + (uint32_t)ch * 16;
-  uint8_t* hi = hi_base + (kb / SW) * plane;
-  const uint32_t kbin = kb % SW;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool ok = affine && i < nval;
-    sc[i] = ok ? s_sc[c + i] : 0.f;
-    sh[i] = ok ? s_sh[c + i] : 0.f;
-  }
-  const float* srcc = src + c;
+  const int cpp = nch >> 3;                             // full chunks per row
+  const int ntail = nch & 7;                            // channels of the partial chunk (even; a multiple of 4 when V == 4)
   const int* tab = src_tab + tab_off;
-  for (int pos = pos0; pos < rows; pos += 2 * dpos) {
-    float v[2][8];
-    int px[2];
+  if (cpp > 0) {
+    const int dpos = TS / cpp;                          // rows advanced per step (TS >= 128 >= cpp)
+    if (t < dpos * cpp) {
+      const int pos0 = t / cpp, ch = t - pos0 * cpp;
+      const int c = c_first + ch * 8;
+      const uint32_t kb = byte0 + (uint32_t)ch * 16;
+      uint8_t* hi = hi_base + (kb / SW) * plane;
+      const uint32_t kbin = kb % SW;
+      float sc[8], sh[8];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int pp = pos + u * dpos;
-      px[u] = pp < rows ? tab[pp * tab_stride] : -2;
+      for (int i = 0; i < 8; ++i) {
+        sc[i] = affine ? s_sc[c + i] : 0.f;
+        sh[i] = affine ? s_sh[c + i] : 0.f;
+      }
+      const float* srcc = src + c;
+      for (int pos = pos0; pos < rows; pos += 2 * dpos) {
+        float v[2][8];
+        int px[2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
-      if (px[u] >= 0) {
-        const float* xp = srcc + (long)px[u] * C;
-        if (V == 4) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(xp));
-          v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
-          if (nval > 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(xp + 4));
-            v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+        for (int u = 0; u < 2; ++u) {
+          const int pp = pos + u * dpos;
+          px[u] = pp < rows ? tab[pp * tab_stride] : -2;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+          if (px[u] >= 0) {
+            const float* xp = srcc + (long)px[u] * C;
+            if (V == 4) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(xp));
+              const float4 b = __ldg(reinterpret_cast<const float4*>(xp + 4));
+              v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
+              v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(xp + 2 * j));
+                v[u][2 * j] = a.x; v[u][2 * j + 1] = a.y;
+              }
+            }
           }
-        } else {
+        }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (2 * j < nval) {
-              const float2 a = __ldg(reinterpret_cast<const float2*>(xp + 2 * j));
-              v[u][2 * j] = a.x; v[u][2 * j + 1] = a.y;
+        for (int u = 0; u < 2; ++u) {
+          if (px[u] == -2) continue;
+          if (affine && px[u] >= 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float a = fmaf(v[u][i], sc[i], sh[i]);
+              v[u][i] = relu ? fmaxf(a, 0.f) : a;
+            }
+          }
+          uint4 h, l;
+          split8(v[u], h, l);
+          const uint32_t off = swz16((uint32_t)(pos + u * dpos), kbin, SW);
+          *reinterpret_cast<uint4*>(hi + off) = h;
+          *reinterpret_cast<uint4*>(hi + lo_off + off) = l;
+        }
+      }
+    }
+  }
+  if (ntail) {
+    // partial chunk: thread t takes rows t, t + TS, ... (two in flight), only the valid channels are loaded / written
+    const int c = c_first + cpp * 8;
+    const uint32_t kb = byte0 + (uint32_t)cpp * 16;
+    uint8_t* hi = hi_base + (kb / SW) * plane;
+    const uint32_t kbin = kb % SW;
+    float sc[6], sh[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const bool ok = affine && i < ntail;
+      sc[i] = ok ? s_sc[c + i] : 1.f;
+      sh[i] = ok ? s_sh[c + i] : 0.f;
+    }
+    const float lo_clamp = relu ? 0.f : -INFINITY;
+    const float* srcc = src + c;
+    const int np = ntail >> 1;                          // channel pairs: 1..3 (V == 4: 2)
+    for (int pos = t; pos < rows; pos += 2 * TS) {
+      float v[2][6];
+      int px[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int pp = pos + u * TS;
+        px[u] = pp < rows ? tab[pp * tab_stride] : -2;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v[u][i] = 0.f;
+        if (px[u] >= 0) {
+          const float* xp = srcc + (long)px[u] * C;
+          if (V == 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(xp));
+            v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              if (j < np) {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(xp + 2 * j));
+                v[u][2 * j] = a.x; v[u][2 * j + 1] = a.y;
+              }
             }
           }
         }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (px[u] == -2) continue;
-      if (affine && px[u] >= 0) {
+      for (int u = 0; u < 2; ++u) {
+        if (px[u] == -2) continue;
+        const uint32_t off = swz16((uint32_t)(pos + u * TS), kbin, SW);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float a = fmaf(v[u][i], sc[i], sh[i]);
-          v[u][i] = relu ? fmaxf(a, 0.f) : a;
+        for (int j = 0; j < 3; ++j) {
+          if (j < np) {
+            uint32_t hw = 0, lw = 0;
+            if (px[u] >= 0) {
+              float a = v[u][2 * j], b = v[u][2 * j + 1];
+              if (affine) { a = fmaxf(fmaf(a, sc[2 * j], sh[2 * j]), lo_clamp); b = fmaxf(fmaf(b, sc[2 * j + 1], sh[2 * j + 1]), lo_clamp); }
+              split2(a, b, hw, lw);
+            }
+            *reinterpret_cast<uint32_t*>(hi + off + 4 * j) = hw;
+            *reinterpret_cast<uint32_t*>(hi + lo_off + off + 4 * j) = lw;
+          }
         }
       }
-      uint4 h, l;
-      split8(v[u], h, l);
-      const uint32_t off = swz16((uint32_t)(pos + u * dpos), kbin, SW);
-      *reinterpret_cast<uint4*>(hi + off) = h;
-      *reinterpret_cast<uint4*>(hi + lo_off + off) = l;
     }
   }
 }

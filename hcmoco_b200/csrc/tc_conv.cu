@@ -29,7 +29,7 @@ constexpr int NTHREADS = NTRANS + 128 + 64;  // then 4 epilogue warps, the TMA p
 // (the SMSP arbiter favours the highest warp id: the single MMA-issuing warp must not starve behind busy transform warps)
 constexpr int W_EPI = NTRANS / 32, W_TMA = W_EPI + 4, W_MMA = W_TMA + 1;
 constexpr int MAXG = 16;
-constexpr int MAX_LPAD = 512;
+constexpr int MAX_LPAD = 1024;
 constexpr int HDR_BYTES = 4096 + 6144 + 2048;   // barriers / tmem ptr / scale / shift | row-concat boundary exchange (2 x 3 warps x 3 rows x 80 floats) | issue schedule (descriptor low words); the per-stage source tables follow
 constexpr int MAX_ASTAGE = 4;
 constexpr int MAX_UNITS = 256;
@@ -44,8 +44,10 @@ struct Geo {
   int rc;            // row-concatenated taps (3x3 stride 1, 3*Npad <= 256): see make_geo
   int NB;            // N of one weight operand: 3*Npad (rc) or Npad
   int TM;            // output positions per tile: 126 (rc) or 128
+  int st;            // tiles per staged fill ("supertile", see make_geo): 1, or 2..4 consecutive tiles sharing one halo
   int ksplit;        // 1, or 2: the filter taps of a tile are split over two CTAs (work unit = (tile, part)); see make_geo
   long Mv, tiles, units;
+  FastDiv fd_hw, fd_wp;   // position decode: / (Hp*Wp), / Wp
   size_t plane_bytes, a_stage_bytes, wslab, wbytes, smem, tab_bytes;
 };
 
@@ -64,8 +66,31 @@ bool rowcat_ok(int Cout, int ks, int stride, int mode) {
   return rowcat_enabled() && mode == 0 && ks == 3 && stride == 1 && 3 * ceil_to(Cout, 16) <= 256;
 }
 
+Geo make_geo1(int B, int H, int W, int Cin, int Cout, int ks, int stride, int mode, int st);
+
+// Supertiles.  A 3x3 tile of 128 flat positions needs a halo of 2*(Wp+1) more staged rows: 262 rows for 128 outputs on the 64x64
+// maps (2.05x), and the transform warps — the instruction-issue hogs of the narrow layers — pay for every one of them.  When one
+// channel group holds the layer (Cin16 * nq <= 64) and shared memory allows, a fill stages `st` CONSECUTIVE tiles at once
+// (st*128 + halo rows: 1.26x at st = 4) and the MMA warp issues the st tiles from row offsets 0, 128, .. of the same staged block;
+// the CTAs then own contiguous tile ranges.  HCM_TC_ST=1 switches it off, =2/3 caps it (experiments).
 Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride, int mode = 0) {
+  static int st_max = -1;
+  if (st_max < 0) { const char* e = getenv("HCM_TC_ST"); st_max = e ? atoi(e) : 4; if (st_max < 1) st_max = 1; if (st_max > 4) st_max = 4; }
+  Geo g1 = make_geo1(B, H, W, Cin, Cout, ks, stride, mode, 1);
+  const bool halo = (mode == 1) || ks == 3;
+  if (!halo || g1.rc || g1.ngroups != 1 || g1.ksplit != 1) return g1;
+  const long tpc = (g1.tiles + 147) / 148;                    // tiles per CTA
+  for (int st = st_max; st >= 2; --st) {
+    if (2 * st > tpc) continue;                               // at least two fills per CTA, or nothing overlaps
+    Geo g = make_geo1(B, H, W, Cin, Cout, ks, stride, mode, st);
+    if (g.ngroups == 1 && g.nastage >= 2 && g.w_resident == g1.w_resident && g.Lpad <= MAX_LPAD && g.smem <= 227 * 1024) return g;
+  }
+  return g1;
+}
+
+Geo make_geo1(int B, int H, int W, int Cin, int Cout, int ks, int stride, int mode, int st) {
   Geo g;
+  g.st = st;
   // Row concatenation: the three taps (r, 0..2) of a filter row share ONE A operand start (row offset r*Wp) and are the
   // N blocks of one weight operand: E_s[m'] = sum_r A[m' + r*Wp] * W_(r,s).  The column shift moves to the epilogue,
   // out[m] = E_0[m] + E_1[m+1] + E_2[m+2] (warp shuffles + a 3-row exchange between the epilogue warps), so a tile yields
@@ -90,8 +115,10 @@ Geo make_geo(int B, int H, int W, int Cin, int Cout, int ks, int stride, int mod
     g.nqs = (4 * g.Cp <= 256) ? 4 : ((2 * g.Cp <= 256) ? 2 : 1);
   }
   g.Mv = (long)B * g.Hp * g.Wp;
+  g.fd_hw = make_fastdiv((uint32_t)(g.Hp * g.Wp));
+  g.fd_wp = make_fastdiv((uint32_t)g.Wp);
   g.tiles = (g.Mv + g.TM - 1) / g.TM;
-  g.Lpad = ceil_to(g.L, 16);
+  g.Lpad = ceil_to((st - 1) * g.TM + g.L, 16);
   g.Npad = (mode == 1) ? g.nqs * g.Cp : ceil_to(Cout, 16);
   g.Cin16 = ceil_to(Cin, 16);
   g.SC = g.nq * g.Cin16;                      // staged channels per position
@@ -191,6 +218,7 @@ struct TcParams {
   int B, H, W, Cin, Cout;
   int q0;                      // mode 1: first output parity of this launch
   long long* dbg;
+  int dbg_mode;                // HCM_TC_DBGMODE experiments: 1 transform skips staging, 2 epilogue skips stores, 4 epilogue skips TMEM loads too
   Geo g;
   // host-built issue schedule: steps ordered (group, tap, K16 step); x = byte offset of the A operand inside a stage,
   // y = weight slab index.  The MMA warp reads it from the constant bank (uniform loads): the issue loop must stay lean,
@@ -250,8 +278,8 @@ __device__ __forceinline__ int virt_to_src(long pv, int q, const TcParams& p) {
   if (pv < 0 || pv >= g.Mv) return -1;
   if (g.mode == 0 && g.ks == 1) return (int)pv;
   const unsigned v = (unsigned)pv, hw = (unsigned)(g.Hp * g.Wp);
-  const unsigned b = v / hw, rem = v - b * hw;
-  const unsigned row = rem / (unsigned)g.Wp, col = rem - row * (unsigned)g.Wp;
+  const unsigned b = fdiv(v, g.fd_hw), rem = v - b * hw;
+  const unsigned row = fdiv(rem, g.fd_wp), col = rem - row * (unsigned)g.Wp;
   if (g.mode == 1) {
     if (row >= (unsigned)g.Ho || col >= (unsigned)g.Wo) return -1;
     return (int)((b * g.Ho + row) * g.Wo + col);
@@ -270,8 +298,8 @@ __device__ __forceinline__ int virt_to_dst(long pv, const TcParams& p) {
   if (pv < 0 || pv >= g.Mv) return -1;
   if (g.mode == 0 && g.ks == 1) return (int)pv;
   const unsigned v = (unsigned)pv, hw = (unsigned)(g.Hp * g.Wp);
-  const unsigned b = v / hw, rem = v - b * hw;
-  const unsigned row = rem / (unsigned)g.Wp, col = rem - row * (unsigned)g.Wp;
+  const unsigned b = fdiv(v, g.fd_hw), rem = v - b * hw;
+  const unsigned row = fdiv(rem, g.fd_wp), col = rem - row * (unsigned)g.Wp;
   if (g.mode == 1) {
     if (row >= (unsigned)g.Ho || col >= (unsigned)g.Wo) return -1;
     return (int)((b * p.H + 2 * row) * p.W + 2 * col);
@@ -302,6 +330,7 @@ __device__ __forceinline__ uint64_t with_addr(uint64_t templ, uint32_t saddr) { 
 __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Geo& g = p.g;
+  if (p.dbg && threadIdx.x == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(long)blockIdx.x * 16 + 8] = t; }
   // barriers: 0..3 a_full  4..7 a_empty  8,9 acc_full  10,11 acc_empty  12 w_full(resident)  16..31 ring full, 32..47 ring empty
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + 512);
@@ -350,9 +379,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  if (p.dbg && threadIdx.x == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(long)blockIdx.x * 16 + 9] = t; }
 
-  const int my_tiles = (int)((g.units - blockIdx.x + gridDim.x - 1) / gridDim.x);   // work units (tile, part) of this CTA
   const int ksplit = g.ksplit;
+  const int st = g.st;                                                   // tiles per fill; > 1: this CTA owns a contiguous tile range
+  const long t_first = (st > 1) ? ((long)blockIdx.x * g.tiles) / gridDim.x : 0;
+  const int my_tiles = (st > 1) ? (int)(((long)(blockIdx.x + 1) * g.tiles) / gridDim.x - t_first)
+                                : (int)((g.units - blockIdx.x + gridDim.x - 1) / gridDim.x);   // work units (tile, part) of this CTA
+  // supertile fills ramp up (1, 2, st, st, .. tiles) so that the first MMA does not wait for a whole st-tile halo
+  const int st_r1 = min(2, st);
+  auto fill_first = [&](int f) -> int { return f == 0 ? 0 : (f == 1 ? 1 : 1 + st_r1 + (f - 2) * st); };
+  auto fill_size = [&](int f) -> int { return min(f == 0 ? 1 : (f == 1 ? st_r1 : st), my_tiles - fill_first(f)); };
+  // first virtual position of the CTA's ti-th tile
+  auto tile_pos = [&](int ti) -> long {
+    if (st > 1) return (t_first + ti) * g.TM;
+    const unsigned unit = blockIdx.x + (unsigned)ti * gridDim.x;
+    return (long)((ksplit == 2) ? (unit >> 1) : unit) * g.TM;
+  };
   const int nj = g.Cin16 / 16;                                           // K=16 steps per tap
   (void)nj;
 
@@ -366,19 +409,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
           tma_bulk_g2s(smem_u32(Wbase + off), p.wpack + off, n, BAR(12));
         }
       } else {
-        long it = 0;                                                     // chunk counter
+        int s = 0;                                                       // ring slot and its phase (no per-chunk divisions)
+        uint32_t ph = 1;
         const uint32_t chunk_bytes = (uint32_t)g.spb * wslab;
         for (int ti = 0; ti < my_tiles; ++ti) {
-          const int part = (int)(((long)blockIdx.x + (long)ti * gridDim.x) % ksplit);
+          const int part = (ksplit == 2) ? (int)((blockIdx.x + (unsigned)ti * gridDim.x) & 1u) : 0;
           const int st_end = p.pstart[part] + p.plen[part];
-          for (int st0 = p.pstart[part]; st0 < st_end; st0 += g.spb, ++it) {
-            const int s = (int)(it % g.wst);
+          for (int st0 = p.pstart[part]; st0 < st_end; st0 += g.spb) {
             const int n = min(g.spb, st_end - st0);
-            mbar_wait(BAR(32 + s), (uint32_t)(((it / g.wst) & 1) ^ 1));
+            mbar_wait(BAR(32 + s), ph);
             mbar_expect_tx(BAR(16 + s), (uint32_t)n * wslab);
             for (int k = 0; k < n; ++k)
               tma_bulk_g2s(smem_u32(Wbase + (size_t)s * chunk_bytes + (size_t)k * wslab),
                            p.wpack + (size_t)p.steps[st0 + k].y * wslab, wslab, BAR(16 + s));
+            if (++s == g.wst) { s = 0; ph ^= 1u; }
           }
         }
       }
@@ -390,29 +434,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     const uint64_t a_t = sw_desc_template(SW);
     const uint32_t b_lbo = (uint32_t)(2 * g.NB) * 16;
     const uint64_t b_t = smem_desc(0, b_lbo, 128);                         // no-swizzle K-major weight slab
-    long long c_acc = 0, c_a = 0, c_all = clock64(), tq;
+    long long c_acc = 0, c_a = 0, c_all = clock64(), tq = 0;
     if (g.w_resident) mbar_wait(BAR(12), 0);
-    long f = 0;
+    // stage / phase counters advance incrementally: this warp is the serial resource of the kernel, and the emulated 64-bit
+    // divisions that used to derive them per tile cost ~1k of its ~3k cycles per tile (HCM_TC_DBGMODE=7 experiment, round 2)
+    const bool dbg = p.dbg != nullptr;
+    int s = 0, as = 0;               // A stage / accumulator stage and their phases
+    uint32_t sph = 0, aph = 1;
     int within = 0, rs = 0;          // weight ring: step inside the current chunk, slot, slot phase
     uint32_t rph = 0;
-    for (int ti = 0; ti < my_tiles; ++ti) {
-      const int as = ti % g.acc_stages;
-      tq = clock64();
-      mbar_wait(BAR(10 + as), (uint32_t)(((ti / g.acc_stages) & 1) ^ 1)); // epilogue has drained this accumulator
-      c_acc += clock64() - tq;
-      tc_fence_after();
-      const uint32_t d = tmem + (uint32_t)(as * g.acc_cols);
-      uint32_t first = 0;                 // accumulate flag of the next MMA (0 = overwrite: first MMA of the tile)
-      const int part = (int)(((long)blockIdx.x + (long)ti * gridDim.x) % ksplit);
+    // st == 1: per tile { wait accumulator; per channel group { wait its staged fill; issue } ; commit accumulator }
+    // st  > 1: one channel group; per fill { wait it; per tile of the fill { wait accumulator; issue from row offset j*128; commit } }
+    for (int ti = 0, fi = 0; ti < my_tiles; ++fi) {
+      const int nsub = (st > 1) ? fill_size(fi) : 1;
+      uint32_t d = 0, first = 0;          // accumulator; accumulate flag of the next MMA (0 = overwrite: first MMA of the tile)
+      const int part = (ksplit == 2) ? (int)((blockIdx.x + (unsigned)ti * gridDim.x) & 1u) : 0;
       int sidx = p.pstart[part];
       const int st_end = sidx + p.plen[part];
-      for (int grp = 0; grp < g.ngroups; ++grp, ++f) {
-        const int s = (int)(f % g.nastage);
-        tq = clock64();
-        mbar_wait(BAR(s), (uint32_t)((f / g.nastage) & 1));
-        c_a += clock64() - tq;
+      if (st == 1) {
+        if (dbg) tq = clock64();
+        mbar_wait(BAR(10 + as), aph);                                     // epilogue has drained this accumulator
+        if (dbg) c_acc += clock64() - tq;
         tc_fence_after();
-        const uint32_t ab = a0 + (uint32_t)s * (uint32_t)g.a_stage_bytes;
+        d = tmem + (uint32_t)(as * g.acc_cols);
+      }
+      for (int grp = 0; grp < g.ngroups; ++grp) {
+        if (dbg) tq = clock64();
+        mbar_wait(BAR(s), sph);
+        if (dbg) c_a += clock64() - tq;
+        tc_fence_after();
+       for (int j = 0; j < nsub; ++j) {
+        if (st > 1) {
+          if (dbg) tq = clock64();
+          mbar_wait(BAR(10 + as), aph);
+          if (dbg) c_acc += clock64() - tq;
+          tc_fence_after();
+          d = tmem + (uint32_t)(as * g.acc_cols);
+          first = 0; sidx = p.pstart[0];
+        }
+        const uint32_t ab = a0 + (uint32_t)s * (uint32_t)g.a_stage_bytes + (uint32_t)(j * TILE_M) * SW;
         const int n = p.gcount[part][grp];
         if (g.w_resident) {
           if (elect_one()) {
@@ -478,9 +538,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
           }
           if (n) first = 1u;
         }
+        if (st > 1) {
+          if (elect_one()) umma_commit(BAR(8 + as));                      // accumulator of this tile complete
+          if (++as == g.acc_stages) { as = 0; aph ^= 1u; }
+        }
+       }
         if (elect_one()) umma_commit(BAR(4 + s));                         // staged A buffer free
+        if (++s == g.nastage) { s = 0; sph ^= 1u; }
       }
-      if (elect_one()) umma_commit(BAR(8 + as));                          // accumulator complete
+      if (st == 1) {
+        if (elect_one()) umma_commit(BAR(8 + as));                        // accumulator complete
+        if (++as == g.acc_stages) { as = 0; aph ^= 1u; }
+      }
+      ti += nsub;
     }
     if (p.dbg && lane == 0) {
       long long* o = p.dbg + (long)blockIdx.x * 16;
@@ -491,20 +561,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     const int TS = NTRANS / g.nastage;                                    // team size: team k owns A stage k
     const int team = threadIdx.x / TS, t = threadIdx.x - team * TS;
     const int V = g.V;
-    long long c_wait = 0, c_all = clock64(), tq;
-    const long nfills = (long)my_tiles * g.ngroups;
-    for (long f = team; f < nfills; f += g.nastage) {
+    long long c_wait = 0, c_all = clock64(), tq = 0;
+    const bool dbg = p.dbg != nullptr;
+    int nfills = my_tiles * g.ngroups;
+    if (st > 1) nfills = my_tiles <= 1 ? my_tiles : (my_tiles <= 1 + st_r1 ? 2 : 2 + (my_tiles - 1 - st_r1 + st - 1) / st);
+    const int qsh = (g.nq == 4) ? 2 : 0;                                  // nq is 1 or 4
+    // fill f = team + k * nastage -> (tile ti, channel group grp), advanced incrementally (no per-fill divisions);
+    // supertiles (st > 1, one channel group): fill f = tiles [f*st, f*st + nsub)
+    int ti = (st > 1) ? fill_first(team) : team / g.ngroups, grp = (st > 1) ? 0 : team - ti * g.ngroups;
+    uint32_t eph = 1;
+    for (int f = team; f < nfills; f += g.nastage, eph ^= 1u) {
       {
-        const int ti = (int)(f / g.ngroups), grp = (int)(f - (long)ti * g.ngroups);
-        const long tile0 = (((long)blockIdx.x + (long)ti * gridDim.x) / ksplit) * g.TM;
+        const long tile0 = tile_pos(ti);
+        const int nsub = (st > 1) ? fill_size(f) : 1;
+        const int Lf = (nsub - 1) * g.TM + g.L;                           // staged rows of this fill, and padded to the K = 16 steps
+        const int rows_f = min(g.Lpad, (Lf + 15) & ~15);
         const int s = team;
-        tq = clock64();
-        mbar_wait(BAR(4 + s), (uint32_t)(((f / g.nastage) & 1) ^ 1));
-        c_wait += clock64() - tq;
+        if (dbg) tq = clock64();
+        mbar_wait(BAR(4 + s), eph);
+        if (dbg) c_wait += clock64() - tq;
         int* src_tab = s_src + s * tab_stride;
-        for (int e = t; e < g.Lpad * g.nq; e += TS) {
-          const int pos = e / g.nq, q = e - pos * g.nq;
-          src_tab[e] = (pos < g.L) ? virt_to_src(tile0 - g.center + pos, q, p) : -1;
+        for (int e = t; e < rows_f * g.nq; e += TS) {
+          const int pos = e >> qsh, q = e - (pos << qsh);
+          src_tab[e] = (pos < Lf) ? virt_to_src(tile0 - g.center + pos, q, p) : -1;
         }
         asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TS) : "memory");
         // the real (non-padding) channels of this group, plane by plane (stride 2: four parity planes side by side)
@@ -513,38 +592,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
         for (int q = 0; q < g.nq; ++q) {
           const int a = max(c_lo, q * g.Cin16), b = min(c_hi, q * g.Cin16 + p.Cin);
           if (b <= a) continue;
-          if (V == 4) stage_rows8<4>(p.x, p.Cin, a - q * g.Cin16, b - a, g.Lpad, src_tab, g.nq, q, A_hi, lo_off, plane, SW,
+          if (p.dbg_mode & 1) continue;
+          if (V == 4) stage_rows8<4>(p.x, p.Cin, a - q * g.Cin16, b - a, rows_f, src_tab, g.nq, q, A_hi, lo_off, plane, SW,
                                      (uint32_t)(a - c_lo) * 2, s_sc, s_sh, p.in_scale != nullptr, p.in_relu, t, TS);
-          else stage_rows8<2>(p.x, p.Cin, a - q * g.Cin16, b - a, g.Lpad, src_tab, g.nq, q, A_hi, lo_off, plane, SW,
+          else stage_rows8<2>(p.x, p.Cin, a - q * g.Cin16, b - a, rows_f, src_tab, g.nq, q, A_hi, lo_off, plane, SW,
                               (uint32_t)(a - c_lo) * 2, s_sc, s_sh, p.in_scale != nullptr, p.in_relu, t, TS);
         }
         fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         mbar_arrive(BAR(s));
       }
+      if (st > 1) ti = fill_first(f + g.nastage);
+      else { grp += g.nastage; while (grp >= g.ngroups) { grp -= g.ngroups; ++ti; } }
     }
     if (p.dbg && threadIdx.x == 0) { long long* o = p.dbg + (long)blockIdx.x * 16; o[4] = clock64() - c_all; o[5] = c_wait; }
   } else {
     // ===== epilogue warps: TMEM -> registers -> global (fp32 NHWC), interior positions only =====
     const int q = warp & 3;                             // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
-    long long c_wait = 0, c_all = clock64(), tq;
+    long long c_wait = 0, c_all = clock64(), tq = 0;
+    const bool dbg = p.dbg != nullptr;
     const bool vec4 = (p.Cout % 4) == 0;
+    int as = 0;
+    uint32_t aph = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
-      const long unit = (long)blockIdx.x + (long)ti * gridDim.x;
-      const long tile0 = (unit / ksplit) * g.TM;
+      const unsigned unit = blockIdx.x + (unsigned)ti * gridDim.x;
+      const long tile0 = tile_pos(ti);
       const bool atomic_out = ksplit > 1;                 // split-K: both halves are added onto the zeroed / accumulated output
-      const bool add_bias = p.bias && (unit % ksplit) == 0;
-      const int as = ti % g.acc_stages;
+      const bool add_bias = p.bias && (ksplit == 1 || (unit & 1u) == 0);
       const int px = (m < g.TM) ? virt_to_dst(tile0 + m, p) : -1;   // row-concat tiles: rows 126, 127 belong to the next tile
       float* yp = p.y + (long)(px < 0 ? 0 : px) * p.Cout;   // indexed [c0 + i] below
-      tq = clock64();
-      mbar_wait(BAR(8 + as), (uint32_t)((ti / g.acc_stages) & 1));
-      c_wait += clock64() - tq;
+      if (dbg) tq = clock64();
+      mbar_wait(BAR(8 + as), aph);
+      if (dbg) c_wait += clock64() - tq;
       tc_fence_after();
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * g.acc_cols);
       // row-concat boundary exchange: [tile parity][chunk][warp 1..3][E_1 row 0, E_2 row 0, E_2 row 1][16]
       float* xch = reinterpret_cast<float*>(smem + 4096) + (ti & 1) * (5 * 3 * 3 * 16);
       for (int c0 = 0; c0 < g.Npad; c0 += 16) {
+        if (p.dbg_mode & 4) break;
         if (g.mode == 1) {
           // parity block qq = c0 / Cp of the 2x2 output pixels of this position; channel offset inside the block
           const int qq = p.q0 + c0 / g.Cp, cc = c0 - (c0 / g.Cp) * g.Cp;
@@ -591,7 +676,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
           }
         }
         const int cend = (g.mode == 1) ? (c0 / g.Cp) * g.Cp + p.Cout : p.Cout;      // first invalid column
-        if (px >= 0) {
+        if (px >= 0 && !(p.dbg_mode & 2)) {
           if (add_bias) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) if (c0 + i < cend) v[i] += p.bias[c0 + i];
@@ -622,12 +707,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
       }
       tc_fence_before();
       mbar_arrive(BAR(10 + as));                        // accumulator stage may be overwritten
+      if (++as == g.acc_stages) { as = 0; aph ^= 1u; }
     }
     if (p.dbg && m == 0) { long long* o = p.dbg + (long)blockIdx.x * 16; o[6] = clock64() - c_all; o[7] = c_wait; }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == W_MMA) tmem_dealloc(tmem, g.tmem_cols);
+  if (p.dbg && threadIdx.x == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(long)blockIdx.x * 16 + 10] = t; }
 }
 
 // ------------------------------------------------------------------------------------------ weight packing
@@ -766,6 +853,7 @@ int launch_tc(TcParams& p, cudaStream_t stream, const char* what) {
     if (dbg_on) cudaMalloc(&dbg, 148 * 16 * sizeof(long long));
   }
   p.dbg = dbg;
+  { static int dm = -1; if (dm < 0) { const char* e = getenv("HCM_TC_DBGMODE"); dm = e ? atoi(e) : 0; } p.dbg_mode = dm; }
   if (dbg_on) cudaMemsetAsync(dbg, 0, 148 * 16 * sizeof(long long), stream);
   static bool configured = false;
   if (!configured) {
@@ -779,6 +867,18 @@ int launch_tc(TcParams& p, cudaStream_t stream, const char* what) {
     long long h[148 * 16];
     cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
     const long long* o = h;      // CTA 0
+    {
+      long long s_min = 0, s_max = 0, e_max = 0, pro = 0;
+      for (int c = 0; c < p.g.grid; ++c) {
+        const long long* q = h + c * 16;
+        if (c == 0 || q[8] < s_min) s_min = q[8];
+        if (c == 0 || q[8] > s_max) s_max = q[8];
+        if (c == 0 || q[10] > e_max) e_max = q[10];
+        if (q[9] - q[8] > pro) pro = q[9] - q[8];
+      }
+      fprintf(stderr, "[%s time] span %.2f us (first CTA start -> last CTA end), CTA starts spread %.2f us, prologue (max) %.2f us, CTA0 %.2f us, st %d\n",
+              what, (e_max - s_min) * 1e-3, (s_max - s_min) * 1e-3, pro * 1e-3, (h[10] - h[8]) * 1e-3, p.g.st);
+    }
     fprintf(stderr, "[%s dbg] %dx%d %d->%d mode %d tiles/cta %ld steps %d astages %d resident %d | mma: total %lld wait_acc %lld "
             "wait_a %lld | transform: total %lld wait %lld | epilogue: total %lld wait %lld\n", what, p.H, p.W, p.Cin, p.Cout,
             p.g.mode, (p.g.units + p.g.grid - 1) / p.g.grid, p.g.nsteps, p.g.nastage, p.g.w_resident, o[0], o[2], o[3], o[4],

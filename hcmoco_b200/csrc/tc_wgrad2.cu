@@ -25,6 +25,7 @@ struct WGeo {
   int stride, ks, taps, nq, Hp, Wp, Ho, Wo, center, L, Lpad;
   int CI, nsplit, nblk, SWa, SWd, a_blocks, d_blocks, ntr, tiles_per, tmem_cols, nstage, Va, Vd;
   long Mv, T;
+  FastDiv fd_hw, fd_wp;   // position decode: / (Hp*Wp), / Wp
   size_t a_plane, d_plane, a_bytes, d_bytes, stage_bytes, tab_bytes, smem;
 };
 
@@ -38,6 +39,8 @@ WGeo make_wgeo(int B, int H, int W, int Cin, int Cout, int ks, int stride) {
   else if (stride == 1) { g.Hp = H + 2; g.Wp = W + 2; g.center = g.Wp + 1; g.L = TILE + 2 * (g.Wp + 1); }
   else { g.Hp = g.Ho + 1; g.Wp = g.Wo + 1; g.center = g.Wp + 1; g.L = TILE + g.Wp + 1; }
   g.Mv = (long)B * g.Hp * g.Wp;
+  g.fd_hw = make_fastdiv((uint32_t)(g.Hp * g.Wp));
+  g.fd_wp = make_fastdiv((uint32_t)g.Wp);
   g.T = (g.Mv + TILE - 1) / TILE;
   g.Lpad = ceil_to(g.L, 16);
   g.CI = (ks == 3) ? 32 : 64;                          // input channels per CTA split
@@ -117,8 +120,8 @@ __device__ __forceinline__ void virt_decode(long pv, const WParams& p, int& src0
   if (pv < 0 || pv >= g.Mv) return;
   if (g.ks == 1) { src0 = (int)pv; dst = (int)pv; return; }
   const unsigned v = (unsigned)pv, hw = (unsigned)(g.Hp * g.Wp);
-  const unsigned b = v / hw, rem = v - b * hw;
-  const unsigned row = rem / (unsigned)g.Wp, col = rem - row * (unsigned)g.Wp;
+  const unsigned b = fdiv(v, g.fd_hw), rem = v - b * hw;
+  const unsigned row = fdiv(rem, g.fd_wp), col = rem - row * (unsigned)g.Wp;
   if (g.stride == 1) {
     if (row < 1 || row > (unsigned)p.H || col < 1 || col > (unsigned)p.W) return;
     src0 = (int)((b * p.H + row - 1) * p.W + (col - 1));
@@ -207,18 +210,20 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
       }
     }
     __syncwarp();
-    long long c_all = clock64(), c_wait = 0, tq;
+    long long c_all = clock64(), c_wait = 0, tq = 0;
     // lean issue loop (see umma_bf16_w in tc_common.cuh): descriptor low words = stage base + K-step offset + tap offset
     const uint32_t dy_hi32 = (uint32_t)(dy_t >> 32), a_hi32 = (uint32_t)(a_t >> 32);
     const uint32_t dlo16 = d_lo >> 4, alo16 = a_lo >> 4, kd16 = (16u * SWd) >> 4, ka16 = (16u * SWa) >> 4;
     uint32_t boff16[9], dcolv[9];
 #pragma unroll
     for (int m = 0; m < 9; ++m) { boff16[m] = tap_boff[m] >> 4; dcolv[m] = tmem + tap_col[m]; }
+    const bool dbg = p.dbg != nullptr;
+    int s = 0;                                                   // stage and its phase, advanced incrementally (no divisions)
+    uint32_t sph = 0;
     for (int it = 0; it < ntiles; ++it) {
-      const int s = it % g.nstage;
-      tq = clock64();
-      mbar_wait(BAR(s), (uint32_t)((it / g.nstage) & 1));
-      c_wait += clock64() - tq;
+      if (dbg) tq = clock64();
+      mbar_wait(BAR(s), sph);
+      if (dbg) c_wait += clock64() - tq;
       tc_fence_after();
       const uint32_t st = s0 + (uint32_t)s * (uint32_t)g.stage_bytes;
       if (elect_one()) {
@@ -248,6 +253,7 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
         umma_commit(BAR(4 + s));
       }
       __syncwarp();
+      if (++s == g.nstage) { s = 0; sph ^= 1u; }
     }
     if (elect_one()) umma_commit(BAR(8));
     if (p.dbg && lane == 0) { long long* o = p.dbg + (long)blockIdx.x * 8; o[0] = clock64() - c_all; o[1] = c_wait; }
@@ -255,13 +261,14 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
     // ===== transform teams: team k stages tiles k, k+nstage, ... into stage k =====
     const int TS = NTRANS / g.nstage;
     const int team = threadIdx.x / TS, t = threadIdx.x - team * TS;
-    long long c_all = clock64(), c_wait = 0, c_tab = 0, tq;
-    for (int it = team; it < ntiles; it += g.nstage) {
+    long long c_all = clock64(), c_wait = 0, c_tab = 0, tq = 0;
+    const bool dbg = p.dbg != nullptr;
+    uint32_t eph = 1;
+    for (int it = team; it < ntiles; it += g.nstage, eph ^= 1u) {
       const int s = team;
-      tq = clock64();
-      mbar_wait(BAR(4 + s), (uint32_t)(((it / g.nstage) & 1) ^ 1));
-      c_wait += clock64() - tq;
-      tq = clock64();
+      if (dbg) tq = clock64();
+      mbar_wait(BAR(4 + s), eph);
+      if (dbg) { c_wait += clock64() - tq; tq = clock64(); }
       const long tile0 = (t_beg + it) * TILE;
       int* tab = s_tab + s * tab_stride;
       int* dtab = tab + g.Lpad * g.nq;
@@ -274,7 +281,7 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
         if (m >= 0 && m < TILE) dtab[m] = d;
       }
       asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TS) : "memory");
-      c_tab += clock64() - tq;
+      if (dbg) c_tab += clock64() - tq;
       uint8_t* st = Sbase + (size_t)s * g.stage_bytes;
       // dy tile: channels [co_lo, co_lo + co_n)
       if (g.Vd == 4) stage_rows8<4>(p.dy, p.Cout, co_lo, co_n, TILE, dtab, 1, 0, st, d_lo, (uint32_t)g.d_plane, SWd, 0, nullptr, nullptr, false, 0, t, TS);

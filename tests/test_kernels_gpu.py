@@ -394,6 +394,8 @@ TC_CONVS = [  # B, H, W, Cin, Cout, ks
     (2, 16, 16, 18, 18, 3), (2, 16, 16, 64, 64, 3), (3, 8, 8, 144, 144, 3), (2, 16, 16, 64, 256, 1), (2, 16, 16, 256, 64, 1),
     (2, 16, 16, 256, 18, 3), (2, 32, 32, 36, 36, 3), (4, 64, 64, 18, 18, 3), (2, 8, 8, 72, 18, 1), (1, 12, 12, 256, 256, 3),
     (2, 16, 16, 32, 128, 1), (3, 4, 4, 128, 128, 3), (2, 96, 96, 32, 32, 3),
+    # supertile geometries (several consecutive tiles per staged fill, contiguous tile ranges per CTA): st = 2, 4, 3
+    (16, 64, 64, 18, 18, 3), (40, 64, 64, 18, 18, 3), (13, 96, 96, 32, 32, 3),
 ]
 
 
@@ -462,7 +464,8 @@ def test_tc_wgrad(KK, shape):
 
 
 TC_S2 = [(2, 32, 32, 18, 18), (2, 16, 16, 18, 36), (3, 8, 8, 36, 72), (2, 64, 64, 64, 64), (2, 16, 16, 72, 144), (2, 8, 8, 18, 144),
-         (4, 64, 64, 18, 18), (2, 32, 32, 32, 64), (2, 32, 32, 256, 36), (2, 8, 8, 128, 256), (2, 16, 16, 64, 128)]
+         (4, 64, 64, 18, 18), (2, 32, 32, 32, 64), (2, 32, 32, 256, 36), (2, 8, 8, 128, 256), (2, 16, 16, 64, 128),
+         (64, 64, 64, 18, 36)]       # (the last one: supertiles in the stride-2 data gradient)
 
 
 @pytest.mark.parametrize("shape", TC_S2)
