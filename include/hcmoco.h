@@ -201,6 +201,18 @@ int hcm_joint_mean_bwd(const float* dout, int B, int J, int C, float* dx, int ac
 int hcm_stage_input(const unsigned char* rgb, const unsigned short* depth, const int* crop, const int* flip,
                     const long long* has_depth, int B, int Hs, int Ws, int R, unsigned long long* sums, float* x,
                     float* depth_mask, cudaStream_t stream);
+/* ---- segmentation fine-tuning head (seg_head.cu): learning/segment_trainer.py:722-745 (max of the L2-normalised projection maps),
+ *      networks/fcn.py:108-110 + main_segmentor.py:76-79 (weighted CrossEntropyLoss(ignore_index) on the x4-upsampled logits),
+ *      segment_trainer.py:375-379 (aAcc).  m1, m2, out, d1, d2 [P,128] channels-last (m2 null: one map); inv1, inv2 [P];
+ *      logits / dlogits [P,Cn] (upsampled, Cn <= 64), label [P] int64, acc [4] fp64 scratch, out2 [2] = (loss, aAcc). ---- */
+int hcm_l2norm_max_fwd(const float* m1, const float* m2, long P, int C, float* out, float* inv1, float* inv2,
+                       cudaStream_t stream);
+int hcm_l2norm_max_bwd(const float* dout, const float* m1, const float* m2, const float* inv1, const float* inv2, long P,
+                       int C, float gscale, float* d1, float* d2, int accumulate, cudaStream_t stream);
+int hcm_seg_ce_fwd(const float* logits, const long long* label, const float* class_weight, long P, int Cn, int ignore_index,
+                   double* acc, float* out2, cudaStream_t stream);
+int hcm_seg_ce_bwd(const float* logits, const long long* label, const float* class_weight, long P, int Cn, int ignore_index,
+                   const double* acc, float gscale, float* dlogits, cudaStream_t stream);
 int hcm_sgd_step(float* p, const float* g, float* buf, long n, float lr, float momentum, float wd, int first,
                  float gscale, cudaStream_t stream);
 int hcm_zero(void* p, long bytes, cudaStream_t stream);

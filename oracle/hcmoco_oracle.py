@@ -494,6 +494,51 @@ def scl_loss(G1, G2, joints_yx, use_depth, use_rgb=None, T=0.07):
 # --------------------------------------------------------------------------------------
 # full step (contrast_trainer.py:532-640 first stage, :894-1039 second stage; main_contrast.py:78-81)
 # --------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------ segmentation fine-tuning head
+def fcn_layout(n_class=25, channels=128):
+    """state_dict of networks/build_linear.py:4-15 `FCNHead(128, 128, n_class, num_convs=1, kernel_size=1)` (networks/fcn.py:5-33: the
+    ConvModule registers its BatchNorm as `norm_name` BEFORE its conv)."""
+    c = channels
+    return OrderedDict([
+        ("convs.0.norm_name.weight", (c,)), ("convs.0.norm_name.bias", (c,)), ("convs.0.norm_name.running_mean", (c,)),
+        ("convs.0.norm_name.running_var", (c,)), ("convs.0.norm_name.num_batches_tracked", ()),
+        ("convs.0.conv.weight", (c, c, 1, 1)), ("convs.0.conv.bias", (c,)),
+        ("conv_seg.weight", (n_class, c, 1, 1)), ("conv_seg.bias", (n_class,)),
+    ])
+
+
+def fcn_forward(C, x, train=True):
+    """networks/fcn.py:104-110: conv -> BN(momentum 0.1) -> ReLU -> conv_seg -> bilinear x4 (align_corners=False)."""
+    bk = "convs.0.norm_name."
+    y = F.conv2d(x, C["convs.0.conv.weight"], C["convs.0.conv.bias"])
+    if train:
+        with torch.no_grad():
+            C[bk + "num_batches_tracked"] += 1
+    y = F.batch_norm(y, C[bk + "running_mean"], C[bk + "running_var"], C[bk + "weight"], C[bk + "bias"], train, 0.1, BN_EPS)
+    y = F.relu(y)
+    logits = F.conv2d(y, C["conv_seg.weight"], C["conv_seg.bias"])
+    return F.interpolate(logits, size=(logits.shape[2] * 4, logits.shape[3] * 4), mode="bilinear", align_corners=False)
+
+
+def seg_loss(C, G1, G2, label, true_label, supervise_type=0, class_weights=None, ignore_index=255):
+    """learning/segment_trainer.py:722-748 + main_segmentor.py:76-79 + :375-379.  Returns (loss_seg, aAcc) — (0, 0) with the
+    BN-statistics-only forward of :742-748 when no sample carries a label."""
+    sel = true_label.bool()
+    if int(sel.sum()) == 0 or supervise_type not in (0, 1, 2):
+        tmp = fcn_forward(C, G1)
+        return (tmp - tmp).mean(), torch.zeros(())
+    if supervise_type == 0:
+        a, b = F.normalize(G1[sel], dim=1), F.normalize(G2[sel], dim=1)
+        feat = torch.max(torch.stack([a, b]), 0)[0]
+    else:
+        feat = F.normalize((G1 if supervise_type == 1 else G2)[sel], dim=1)
+    out = fcn_forward(C, feat)
+    lab = label[sel]
+    loss = F.cross_entropy(out, lab, weight=class_weights, ignore_index=ignore_index)
+    aacc = (out.argmax(1) == lab).sum().float() / float(lab.numel())
+    return loss, aacc
+
+
 def make_momentum(P):
     return {k: torch.zeros_like(v) for k, v in P.items() if is_param(k)}
 
@@ -512,7 +557,7 @@ def sgd_step(P, grads, mom, lr=0.03, momentum=0.9, wd=1e-4, first=False):
 
 def train_step(P, mom, banks, batch, nce_idx, dense_idx=None, *, width=18, skeleton="mpii", stage=1,
                T=0.07, nce_m=0.5, lr=0.03, momentum=0.9, wd=1e-4, first=False, all_gather=None,
-               apply_update=True):
+               apply_update=True, seg=None):
     """One pre-train step on one rank.  batch = dict(x, index, skeleton, joints_yx, joints_vis,
     use_depth, depth_mask).  Returns dict of losses/accs/f/grads."""
     for k, v in P.items():
@@ -536,8 +581,29 @@ def train_step(P, mom, banks, batch, nce_idx, dense_idx=None, *, width=18, skele
         res.update(dense_losses=[l.detach() for l in dl], dense_accs=da,
                    joint_losses=[l.detach() for l in jl], joint_accs=ja, scl_loss=sl.detach(),
                    linear_merge1=G1.detach(), linear_merge2=G2.detach(), feat3=out["feat3"].detach())
+    if seg is not None:
+        # SegTrainer.train_soft_joint_pri3d (segment_trainer.py:617-824): the same step + 10 * the FCN-head loss.
+        # seg = dict(C=classifier state, mom=its momentum, label [B,R,R], true_label [B], supervise_type, class_weights)
+        Cc = seg["C"]
+        for k, v in Cc.items():
+            if is_param(k):
+                v.requires_grad_(True)
+                v.grad = None
+        ls, aacc = seg_loss(Cc, out["linear_merge1"], out["linear_merge2"], seg["label"], seg["true_label"],
+                            seg.get("supervise_type", 0), seg.get("class_weights"))
+        loss = loss + 10.0 * ls
+        res.update(seg_loss=ls.detach(), seg_aacc=aacc)
     res["loss"] = loss.detach()
     loss.backward()
+    if seg is not None:
+        Cc = seg["C"]
+        cg = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in Cc.items() if is_param(k)}
+        res["seg_grads"] = {k: g.clone() for k, g in cg.items()}
+        if apply_update:
+            sgd_step(Cc, cg, seg["mom"], lr, momentum, wd, first)
+        for k, v in Cc.items():
+            if is_param(k):
+                v.requires_grad_(False)
     grads = {k: v.grad for k, v in P.items() if is_param(k) and v.grad is not None}
     res["grads"] = {k: g.clone() for k, g in grads.items()}
     # bank update with the (all-gathered) features (mem_bank.py:195-199)

@@ -563,6 +563,63 @@ class TorchKernels:
             x[b, 0:3] = ((acc / 255.0 - mean_c) / std_c).permute(2, 0, 1).to(x.dtype)
         return 0
 
+    # ---------------------------------------------------------------- seg_head.cu
+    def l2norm_max_fwd(self, m1, m2, P, C, out, inv1, inv2):
+        a = m1.reshape(P, C)
+        i1 = 1.0 / a.norm(dim=1).clamp(min=1e-12)
+        o = a * i1[:, None]
+        inv1.reshape(-1)[:P] = i1
+        if m2 is not None:
+            b = m2.reshape(P, C)
+            i2 = 1.0 / b.norm(dim=1).clamp(min=1e-12)
+            o = torch.maximum(o, b * i2[:, None])
+            inv2.reshape(-1)[:P] = i2
+        out.reshape(P, C).copy_(o)
+        return 0
+
+    def l2norm_max_bwd(self, dout, m1, m2, inv1, inv2, P, C, gscale, d1, d2, accumulate):
+        g = dout.reshape(P, C) * gscale
+        i1 = inv1.reshape(-1)[:P, None]
+        n1 = m1.reshape(P, C) * i1
+        g1, g2 = g, None
+        if m2 is not None:
+            i2 = inv2.reshape(-1)[:P, None]
+            n2 = m2.reshape(P, C) * i2
+            second = n2 > n1
+            g1, g2 = torch.where(second, torch.zeros_like(g), g), torch.where(second, g, torch.zeros_like(g))
+        r1 = i1 * (g1 - n1 * (g1 * n1).sum(1, keepdim=True))
+        d1.reshape(P, C).copy_(d1.reshape(P, C) + r1 if accumulate else r1)
+        if m2 is not None:
+            r2 = i2 * (g2 - n2 * (g2 * n2).sum(1, keepdim=True))
+            d2.reshape(P, C).copy_(d2.reshape(P, C) + r2 if accumulate else r2)
+        return 0
+
+    def seg_ce_fwd(self, logits, label, cw, P, Cn, ignore_index, acc, out2):
+        l = logits.reshape(P, Cn)
+        y = label.reshape(P)
+        valid = (y != ignore_index) & (y >= 0) & (y < Cn)
+        yc = torch.where(valid, y, torch.zeros_like(y))
+        w = (cw[yc] if cw is not None else torch.ones(P, dtype=l.dtype, device=l.device)) * valid
+        nll = torch.logsumexp(l, 1) - l.gather(1, yc[:, None])[:, 0]
+        acc.zero_()
+        acc[0] = (w * nll).double().sum()
+        acc[1] = w.double().sum()
+        acc[2] = (l.argmax(1) == y).double().sum()
+        out2[0] = (acc[0] / acc[1]) if float(acc[1]) > 0 else 0.0
+        out2[1] = acc[2] / P
+        return 0
+
+    def seg_ce_bwd(self, logits, label, cw, P, Cn, ignore_index, acc, gscale, dlogits):
+        l = logits.reshape(P, Cn)
+        y = label.reshape(P)
+        valid = (y != ignore_index) & (y >= 0) & (y < Cn)
+        yc = torch.where(valid, y, torch.zeros_like(y))
+        w = (cw[yc] if cw is not None else torch.ones(P, dtype=l.dtype, device=l.device)) * valid
+        k = gscale / float(acc[1]) if float(acc[1]) > 0 else 0.0
+        d = torch.softmax(l, 1) - F.one_hot(yc, Cn).to(l.dtype)
+        dlogits.reshape(P, Cn).copy_(d * (w * k)[:, None])
+        return 0
+
     def joint_stats(self, Lr, Ld, vis, use_depth, B, J, rs, lse, fin):
         r = rs.reshape(B, 2, 3)
         ls = lse.reshape(B, 2, J)

@@ -556,3 +556,47 @@ def test_stage_input(KK, R, Hs, Ws):
     # mean-centring: the masked depth of every depth-bearing sample sums to ~0
     for b in range(3):
         assert abs(float(x0[b, 3].double().sum())) / max(1.0, float(s1[b, 1])) < 1e-6
+
+
+@pytest.mark.parametrize("P", [5, 4096, 70001])
+def test_seg_head_kernels(KK, P):
+    """seg_head.cu against its torch statement: the max of the two L2-normalised maps (forward, and backward routing), and the
+    weighted / ignore-index cross entropy with the all-pixel top-1 accuracy."""
+    kc, kr = KK
+    m1, m2 = rnd(P, 128, seed=1), rnd(P, 128, seed=2)
+    m1[0] = 0.0                                              # a zero row: the eps clamp of F.normalize
+    for mb in (m2, None):
+        outs = []
+        for kk in (kc, kr):
+            out, i1, i2 = torch.empty(P, 128, device=DEV), torch.empty(P, device=DEV), torch.empty(P, device=DEV)
+            kk.l2norm_max_fwd(m1, mb, P, 128, out, i1, i2 if mb is not None else None)
+            g = rnd(P, 128, seed=3)
+            d1, d2 = rnd(P, 128, seed=4), rnd(P, 128, seed=5)
+            kk.l2norm_max_bwd(g, m1, mb, i1, i2 if mb is not None else None, P, 128, 0.7, d1, d2 if mb is not None else None, 1)
+            outs.append((out, i1[1:], d1[1:], d2[1:] if mb is not None else d1[1:]))
+        torch.cuda.synchronize()
+        for a, b in zip(*outs):
+            assert rel(a, b) < TOL, rel(a, b)
+    Cn = 25
+    logits = rnd(P, Cn, seed=7, scale=3.0)
+    g = torch.Generator().manual_seed(P)
+    label = torch.randint(0, Cn, (P,), generator=g)
+    label[torch.rand(P, generator=g) < 0.2] = 255
+    label = label.to(DEV)
+    cw = (torch.rand(Cn, generator=g) * 40 + 1).to(DEV)
+    res = []
+    for kk in (kc, kr):
+        acc, out2, dl = torch.zeros(4, dtype=torch.float64, device=DEV), torch.empty(2, device=DEV), torch.empty(P, Cn, device=DEV)
+        kk.seg_ce_fwd(logits, label, cw, P, Cn, 255, acc, out2)
+        kk.seg_ce_bwd(logits, label, cw, P, Cn, 255, acc, 10.0, dl)
+        res.append((acc[:3], out2, dl))
+    torch.cuda.synchronize()
+    assert rel(res[0][0], res[1][0]) < 1e-6 and float(res[0][0][2]) == float(res[1][0][2])       # hit count exact
+    assert rel(res[0][1], res[1][1]) < 1e-6
+    assert rel(res[0][2], res[1][2]) < TOL
+    # all pixels ignored: loss 0, zero gradient (torch gives NaN)
+    acc, out2, dl = torch.zeros(4, dtype=torch.float64, device=DEV), torch.empty(2, device=DEV), torch.empty(P, Cn, device=DEV)
+    ign = torch.full((P,), 255, dtype=torch.int64, device=DEV)
+    kc.seg_ce_fwd(logits, ign, cw, P, Cn, 255, acc, out2)
+    kc.seg_ce_bwd(logits, ign, cw, P, Cn, 255, acc, 10.0, dl)
+    assert float(out2[0]) == 0.0 and float(dl.abs().max()) == 0.0

@@ -85,3 +85,32 @@ def test_oracle_matches_reference_golden(name):
     for bk, rows, nrm in zip(banks, fin["bank_rows"], fin["bank_norm"]):
         assert _rel(bk[touched], rows) < 2e-4
         assert abs(float(bk.norm()) - nrm) / nrm < 1e-5
+
+
+def test_oracle_seg_head_matches_reference():
+    """oracle.seg_loss / fcn_forward (restating networks/fcn.py + learning/segment_trainer.py:722-748) against the fixture written by
+    tests/golden/make_golden_seg.py from the reference's own FCNHead, nn.CrossEntropyLoss and eval_seg_aacc."""
+    gold = torch.load(os.path.join(GOLD, "seg_head.pt"), weights_only=False)
+    lay = O.fcn_layout(25)
+    assert [k for k, _ in gold["keys"]] == list(lay.keys())
+    assert [tuple(s) for _, s in gold["keys"]] == [tuple(s) for s in lay.values()]
+    for case in gold["cases"]:
+        C = {k: v.clone() for k, v in case["state"].items()}
+        for k, v in C.items():
+            if O.is_param(k):
+                v.requires_grad_(True)
+        G1, G2 = gold["G1"].clone().requires_grad_(True), gold["G2"].clone().requires_grad_(True)
+        loss, aacc = O.seg_loss(C, G1, G2, gold["label"], case["true_label"], case["supervise_type"], gold["class_weights"])
+        (10.0 * loss).backward()
+        assert abs(float(loss) - float(case["loss_seg"])) <= 2e-5 * max(1.0, abs(float(case["loss_seg"])))
+        assert abs(float(aacc) - float(case["aacc"])) < 1e-6
+        for g, ref in ((G1.grad, case["d1"]), (G2.grad, case["d2"])):
+            g = torch.zeros_like(ref) if g is None else g
+            assert _rel(g, ref) < 2e-4 or float(ref.abs().max()) == 0.0
+        for k, ref in case["grads"].items():
+            g = C[k].grad if C[k].grad is not None else torch.zeros_like(C[k])
+            # (the conv bias in front of a train-mode BatchNorm has an exactly-zero gradient: only rounding noise on both sides)
+            assert _rel(g, ref) < 2e-4 or float(ref.abs().max()) < 1e-5, k
+        assert _rel(C["convs.0.norm_name.running_mean"], case["running_mean"]) < 1e-5
+        assert _rel(C["convs.0.norm_name.running_var"], case["running_var"]) < 1e-5
+        assert int(C["convs.0.norm_name.num_batches_tracked"]) == case["nbt"]
