@@ -213,6 +213,25 @@ int hcm_seg_ce_fwd(const float* logits, const long long* label, const float* cla
                    double* acc, float* out2, cudaStream_t stream);
 int hcm_seg_ce_bwd(const float* logits, const long long* label, const float* class_weight, long P, int Cn, int ignore_index,
                    const double* acc, float gscale, float* dlogits, cudaStream_t stream);
+/* ---- PointNet++ primitives (pointnet2.cu): the nine entry points of the reference's native extension `pointnet2_cuda`
+ *      (networks/pointnet2/src/pointnet2_api.cpp:10-23), same argument meaning, raw device pointers instead of at::Tensor, int32
+ *      indices, results identical to the reference kernels (ties included).  xyz / new_xyz / unknown / known [B,*,3];
+ *      points [B,C,N] channel-major; the *_grad entry points ADD into a buffer the caller zeroed (pointnet2_utils.py:66,146,190). ---- */
+int hcm_pn2_furthest_point_sampling(const float* xyz, int B, int N, int M, int* idx, cudaStream_t stream);
+int hcm_pn2_ball_query(const float* new_xyz, const float* xyz, int B, int N, int M, float radius, int nsample, int* idx,
+                       cudaStream_t stream);
+int hcm_pn2_three_nn(const float* unknown, const float* known, int B, int n, int m, float* dist2, int* idx, cudaStream_t stream);
+int hcm_pn2_three_interpolate(const float* points, const int* idx, const float* weight, int B, int C, int m, int n, float* out,
+                              cudaStream_t stream);
+int hcm_pn2_three_interpolate_grad(const float* grad_out, const int* idx, const float* weight, int B, int C, int n, int m,
+                                   float* grad_points, cudaStream_t stream);
+int hcm_pn2_group_points(const float* points, const int* idx, int B, int C, int N, int npoint, int nsample, float* out,
+                         cudaStream_t stream);
+int hcm_pn2_group_points_grad(const float* grad_out, const int* idx, int B, int C, int N, int npoint, int nsample,
+                              float* grad_points, cudaStream_t stream);
+int hcm_pn2_gather_points(const float* points, const int* idx, int B, int C, int N, int npoint, float* out, cudaStream_t stream);
+int hcm_pn2_gather_points_grad(const float* grad_out, const int* idx, int B, int C, int N, int npoint, float* grad_points,
+                               cudaStream_t stream);
 int hcm_sgd_step(float* p, const float* g, float* buf, long n, float lr, float momentum, float wd, int first,
                  float gscale, cudaStream_t stream);
 int hcm_zero(void* p, long bytes, cudaStream_t stream);

@@ -620,6 +620,57 @@ class TorchKernels:
         dlogits.reshape(P, Cn).copy_(d * (w * k)[:, None])
         return 0
 
+    # ---------------------------------------------------------------- pointnet2.cu (statement: oracle/pn2_oracle.py, numpy)
+    def pn2_furthest_point_sampling(self, xyz, B, N, M, idx):
+        from oracle import pn2_oracle as PO
+        idx.copy_(torch.from_numpy(PO.furthest_point_sampling(xyz.detach().cpu().numpy().reshape(B, N, 3), M)))
+        return 0
+
+    def pn2_ball_query(self, new_xyz, xyz, B, N, M, radius, nsample, idx):
+        from oracle import pn2_oracle as PO
+        idx.copy_(torch.from_numpy(PO.ball_query(radius, nsample, xyz.detach().cpu().numpy(), new_xyz.detach().cpu().numpy())))
+        return 0
+
+    def pn2_three_nn(self, unknown, known, B, n, m, dist2, idx):
+        from oracle import pn2_oracle as PO
+        d, i = PO.three_nn(unknown.detach().cpu().numpy(), known.detach().cpu().numpy())
+        dist2.copy_(torch.from_numpy(d))
+        idx.copy_(torch.from_numpy(i))
+        return 0
+
+    def pn2_three_interpolate(self, points, idx, weight, B, C, m, n, out):
+        from oracle import pn2_oracle as PO
+        out.copy_(torch.from_numpy(PO.three_interpolate(points.detach().cpu().numpy(), idx.cpu().numpy(), weight.detach().cpu().numpy())))
+        return 0
+
+    def pn2_three_interpolate_grad(self, grad_out, idx, weight, B, C, n, m, grad_points):
+        from oracle import pn2_oracle as PO
+        g = grad_out.detach().cpu().numpy()[:, :, :, None] * weight.detach().cpu().numpy()[:, None, :, :]
+        grad_points.add_(torch.from_numpy(PO.scatter_add(g.reshape(B, C, n * 3), idx.cpu().numpy().reshape(B, n * 3), m)).to(grad_points.dtype))
+        return 0
+
+    def pn2_group_points(self, points, idx, B, C, N, npoint, nsample, out):
+        from oracle import pn2_oracle as PO
+        out.copy_(torch.from_numpy(PO.group_points(points.detach().cpu().numpy(), idx.cpu().numpy())))
+        return 0
+
+    def pn2_group_points_grad(self, grad_out, idx, B, C, N, npoint, nsample, grad_points):
+        from oracle import pn2_oracle as PO
+        g = PO.scatter_add(grad_out.detach().cpu().numpy().reshape(B, C, npoint * nsample), idx.cpu().numpy().reshape(B, -1), N)
+        grad_points.add_(torch.from_numpy(g).to(grad_points.dtype))
+        return 0
+
+    def pn2_gather_points(self, points, idx, B, C, N, npoint, out):
+        from oracle import pn2_oracle as PO
+        out.copy_(torch.from_numpy(PO.gather_points(points.detach().cpu().numpy(), idx.cpu().numpy())))
+        return 0
+
+    def pn2_gather_points_grad(self, grad_out, idx, B, C, N, npoint, grad_points):
+        from oracle import pn2_oracle as PO
+        g = PO.scatter_add(grad_out.detach().cpu().numpy(), idx.cpu().numpy(), N)
+        grad_points.add_(torch.from_numpy(g).to(grad_points.dtype))
+        return 0
+
     def joint_stats(self, Lr, Ld, vis, use_depth, B, J, rs, lse, fin):
         r = rs.reshape(B, 2, 3)
         ls = lse.reshape(B, 2, J)
