@@ -339,7 +339,7 @@ def replicas_identical(step, dist, world):
     e = step.eng
     sums = []
     for t in (e.store.p, e.store.m, e.banks[0], e.banks[1], e.banks[2]):
-        v = t.view(torch.int32).to(torch.int64)
+        v = t.reshape(-1).view(torch.int32).to(torch.int64)
         sums += [v.sum(), (v * (torch.arange(v.numel(), device=v.device) % 8191 + 1)).sum()]
     mine = torch.stack(sums)
     allv = torch.empty(world, mine.numel(), dtype=torch.int64, device="cuda")

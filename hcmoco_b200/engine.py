@@ -1039,6 +1039,28 @@ class Engine:
         self.store.restore_buffers(saved)
         return self
 
+    def capture_parts(self):
+        """Three CUDA graphs instead of one — forward (model + loss kernels), loss part of the backward (writes d(loss)/d(outputs):
+        embedding, skeleton-feature and projection-map gradients), model part of the backward — so that a caller can add its own
+        gradient to the projection maps between the second and the third (the segmentation head of `segment.SegTrainer`, whose
+        batch of labelled samples changes size from step to step and therefore launches eagerly)."""
+        saved = self.store.save_buffers()
+        self.forward()
+        self.backward()
+        self.store.restore_buffers(saved)
+        torch.cuda.synchronize()
+        K, st, p = self.K, self.store, self.plan
+        self.graph_parts = [torch.cuda.CUDAGraph() for _ in range(3)]
+        with torch.cuda.graph(self.graph_parts[0]):
+            self.forward()
+        with torch.cuda.graph(self.graph_parts[1]):
+            K.zero(st.g, st.n * st.g.element_size())
+            p.run(p.bwd[:self.n_loss_bwd], self.two_streams)
+        with torch.cuda.graph(self.graph_parts[2]):
+            p.run(p.bwd[self.n_loss_bwd:], self.two_streams)
+        self.store.restore_buffers(saved)
+        return self
+
     def step_graph(self, lr=0.03, momentum=0.9, wd=1e-4):
         self.graph.replay()
         self.update_banks()

@@ -310,7 +310,15 @@ class SegTrainer(ContrastTrainer):
         sel = torch.nonzero(data[10].to(K.device) != 0).reshape(-1)
         st_type = int(getattr(a, "supervise_type", 0))
         # forward: encoders + the four contrastive objectives (the engine's program), then the head
-        eng.forward()
+        graphs = None
+        if eng.x.is_cuda and getattr(a, "cuda_graph", True):
+            if not hasattr(eng, "graph_parts"):
+                eng.capture_parts()
+            graphs = eng.graph_parts
+        if graphs is not None:
+            graphs[0].replay()
+        else:
+            eng.forward()
         head.zero_grad()
         out2 = None
         if sel.numel() > 0 and st_type in (0, 1, 2):
@@ -320,12 +328,18 @@ class SegTrainer(ContrastTrainer):
             head.forward_only(eng.lm1.data)
             d1 = d2 = None
         # backward: loss part (writes the map gradients), + the head's, then the model part
-        K.zero(eng.store.g, eng.store.n * eng.store.g.element_size())
-        eng.plan.run(eng.plan.bwd[:eng.n_loss_bwd], eng.two_streams)
+        if graphs is not None:
+            graphs[1].replay()
+        else:
+            K.zero(eng.store.g, eng.store.n * eng.store.g.element_size())
+            eng.plan.run(eng.plan.bwd[:eng.n_loss_bwd], eng.two_streams)
         for act, d in ((eng.lm1, d1), (eng.lm2, d2)):
             if d is not None:
                 act.grad.index_add_(0, sel, d)
-        eng.plan.run(eng.plan.bwd[eng.n_loss_bwd:], eng.two_streams)
+        if graphs is not None:
+            graphs[2].replay()
+        else:
+            eng.plan.run(eng.plan.bwd[eng.n_loss_bwd:], eng.two_streams)
         if world > 1:
             h1 = dist.all_reduce(eng.store.g, async_op=True)
             h2 = dist.all_reduce(head.store.g, async_op=True)

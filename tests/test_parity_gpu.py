@@ -444,7 +444,8 @@ def test_seg_head_matches_oracle_and_reference_golden_gpu(K):
         assert rel(sd["convs.0.norm_name.running_var"], case["running_var"]) < 1e-4
 
 
-def test_seg_step_matches_oracle_gpu(K):
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph_parts"])
+def test_seg_step_matches_oracle_gpu(K, graph):
     """The fused fine-tuning step (engine programs + head + SGD on both stores) on the GPU against oracle.train_step(seg=...), at the
     reference's map size (64x64 maps, 256x256 labels): losses 1e-3; the classifier's gradients 1e-2 (with IDENTICAL maps they agree to
     1e-3, see the test above; here the maps differ by ~1e-5 between engine and oracle, which flips the branch of
@@ -460,7 +461,7 @@ def test_seg_step_matches_oracle_gpu(K):
     opt = SimpleNamespace(modal="RGBD2S", arch="HRNet", jigsaw=False, head="linear", pool_method="mean", width=18, linear_feat_map=1,
                           skeleton_meta_name="mpii", in_channel_list=[3, 3], feat_dim=128, mem="bank+jointspri3d", nce_k=cfg["K"],
                           nce_t=0.07, nce_m=0.5, temperature=0.07, pri3d_num_samples_per_image=cfg["S"], modality_missing=1,
-                          supervise_type=0, cmc_loss_weights=1, other_loss_weights=1, print_freq=1, n_class=25, cuda_graph=False)
+                          supervise_type=0, cmc_loss_weights=1, other_loss_weights=1, print_freq=1, n_class=25, cuda_graph=graph)
     model = HCMoCoModel(opt, K)
     model.store.load_state_dict(P)
     mem = HCMoCoMem(128, cfg["n"], cfg["K"], 0.07, 0.5, K)
