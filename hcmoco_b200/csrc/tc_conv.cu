@@ -326,6 +326,18 @@ __device__ __forceinline__ uint64_t sw_desc_template(uint32_t SW) {
 }
 __device__ __forceinline__ uint64_t with_addr(uint64_t templ, uint32_t saddr) { return templ | (uint64_t)((saddr & 0x3FFFFu) >> 4); }
 
+// Accumulating epilogue (the data gradient of a layer whose input already holds another gradient contribution — every block's
+// first convolution — and the partial sums of the projection): `y += v` as a vector reduction at the L2 (`red.global.add.v4.f32`,
+// fire-and-forget) instead of load + add + store.  Each output element has exactly one writer per launch, so the result is the same
+// single fp32 addition; but the load version exposed a full L2 / HBM round trip per 16-column chunk in the four epilogue warps —
+// measured (B200, B=64): 64x64 18->18 41 -> 88 us, 64x64 64->256 (1x1) 117 -> 406 us with accumulate = 1 (scripts/time_acc.py).
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* p, float2 v) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -689,8 +701,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
             for (int i = 0; i < 16; i += 4) {
               if (c0 + i < cend) {
                 float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                if (p.accumulate) { const float4 old = *reinterpret_cast<const float4*>(yp + c0 + i); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                *reinterpret_cast<float4*>(yp + c0 + i) = o;
+                if (p.accumulate) red_add_v4(yp + c0 + i, o);
+                else *reinterpret_cast<float4*>(yp + c0 + i) = o;
               }
             }
           } else {
@@ -698,8 +710,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
             for (int i = 0; i < 16; i += 2) {
               if (c0 + i < cend) {
                 float2 o = make_float2(v[i], v[i + 1]);
-                if (p.accumulate) { const float2 old = *reinterpret_cast<const float2*>(yp + c0 + i); o.x += old.x; o.y += old.y; }
-                *reinterpret_cast<float2*>(yp + c0 + i) = o;
+                if (p.accumulate) red_add_v2(yp + c0 + i, o);
+                else *reinterpret_cast<float2*>(yp + c0 + i) = o;
               }
             }
           }
