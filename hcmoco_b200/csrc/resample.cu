@@ -150,12 +150,13 @@ __global__ void upsample_adjoint_rows_kernel(const float* __restrict__ g, float*
 }
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int Ctot, long HW, int coff,
-                                    int Cn) {
+                                    int Cn, int Cpad) {
   const long total = (long)B * HW;
   const long stride = (long)gridDim.x * blockDim.x;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
     const long b = e / HW, pix = e - b * HW;
-    for (int c = 0; c < Cn; ++c) out[e * Cn + c] = x[(b * Ctot + coff + c) * HW + pix];
+    for (int c = 0; c < Cn; ++c) out[e * Cpad + c] = x[(b * Ctot + coff + c) * HW + pix];
+    for (int c = Cn; c < Cpad; ++c) out[e * Cpad + c] = 0.f;
   }
 }
 
@@ -202,8 +203,17 @@ extern "C" {
 // out[B,HW,Cn] (NHWC) = x[B, coff:coff+Cn, HW] (NCHW)
 int hcm_nchw_to_nhwc(const float* x, float* out, int B, int Ctot, long HW, int coff, int Cn, cudaStream_t stream) {
   HCM_CHECK_ARG(x && out && coff + Cn <= Ctot, "nchw_to_nhwc: bad args");
-  nchw_to_nhwc_kernel<<<ew_grid((long)B * HW * 4), 256, 0, stream>>>(x, out, B, Ctot, HW, coff, Cn);
+  nchw_to_nhwc_kernel<<<ew_grid((long)B * HW * 4), 256, 0, stream>>>(x, out, B, Ctot, HW, coff, Cn, Cn);
   HCM_LAUNCH_CHECK("nchw_to_nhwc");
+  return HCM_OK;
+}
+
+// the same with the channels of `out` zero-padded to Cpad (out [B,HW,Cpad]): the 3-channel RGB / depth planes become 4-channel
+// rows (16-byte aligned, even channel count) so that the stem convolution runs on the tensor-core kernels
+int hcm_nchw_to_nhwc_pad(const float* x, float* out, int B, int Ctot, long HW, int coff, int Cn, int Cpad, cudaStream_t stream) {
+  HCM_CHECK_ARG(x && out && coff + Cn <= Ctot && Cpad >= Cn, "nchw_to_nhwc_pad: bad args");
+  nchw_to_nhwc_kernel<<<ew_grid((long)B * HW * 4), 256, 0, stream>>>(x, out, B, Ctot, HW, coff, Cn, Cpad);
+  HCM_LAUNCH_CHECK("nchw_to_nhwc_pad");
   return HCM_OK;
 }
 

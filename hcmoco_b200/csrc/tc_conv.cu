@@ -746,7 +746,9 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, uint8_t* __restrict_
     const int n = e >> 4, k = e & 15;
     const int c = 16 * j + k;
     float v = 0.f;
-    if (n < Cout && c < Cin)
+    // (forward packs only: wCin < Cin means the weight tensor has wCin input channels and the GEMM's K is zero-padded to Cin —
+    //  the 3-channel stem run on a 4-channel padded input)
+    if (n < Cout && c < Cin && (transpose || c < wCin))
       v = transpose ? w[((long)c * wCin + n) * g.taps + (g.taps - 1 - tap)] : w[((long)n * wCin + c) * g.taps + tap];
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
@@ -832,7 +834,8 @@ __global__ void tc_pack_batch_kernel(const PackJob* __restrict__ jobs, int njobs
       if (r >= 0 && sx >= 0 && ci < Cin && co < Cout) v = w[(((long)co * Cin + ci) * 3 + r) * 3 + sx];
     } else {
       const int c = 16 * j + k;
-      if (n < Cout && c < Cin) v = mode == 1 ? w[((long)c * wCin + n) * taps + (taps - 1 - tap)] : w[((long)n * wCin + c) * taps + tap];
+      if (n < Cout && c < Cin && (mode == 1 || c < wCin))
+        v = mode == 1 ? w[((long)c * wCin + n) * taps + (taps - 1 - tap)] : w[((long)n * wCin + c) * taps + tap];
     }
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
@@ -976,7 +979,8 @@ long hcm_tc_conv_wpack_bytes(int B, int H, int W, int Cin, int Cout, int ks) {
 int hcm_tc_conv_rowcat_supported(int Cout, int ks, int stride) { return rowcat_ok(Cout, ks, stride, 0) ? 1 : 0; }
 
 // Pack OIHW fp32 weights into the bf16 hi/lo K-step slabs.  `w` may point at a column block of a wider
-// [O][ldw][ks][ks] tensor (ldw = 0: contiguous).  (Cin, Cout) describe the GEMM being run.  flags:
+// [O][ldw][ks][ks] tensor (ldw = 0: contiguous; forward packs with 0 < ldw < Cin: the tensor has only ldw input channels and the
+// GEMM's K is zero-padded to Cin, for an input stored with padded channels).  (Cin, Cout) describe the GEMM being run.  flags:
 //   bit 0 (1): transpose -> the data gradient of a STRIDE-1 conv, i.e. a conv with Cin' = Cout(w), Cout' = Cin(w): pass
 //              Cin = Cout(w), Cout = Cin(w);  clear -> the forward conv of w[Cout][Cin][ks][ks] (any stride)
 //   bit 2 (4): row-concatenated layout, required iff hcm_tc_conv_rowcat_supported(Cout, ks, stride of the consumer)

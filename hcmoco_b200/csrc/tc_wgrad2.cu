@@ -316,7 +316,9 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
     // the dy_lo products of the same channels (see `fold` in the MMA warp)
     const int cr = (m < co_n) ? m : ((g.d_blocks == 1 && m >= bw && m - bw < co_n) ? m - bw : -1);
     const bool rowok = cr >= 0 && ntiles > 0;
-    const int RL = ci_n * g.taps, RLp = RL | 1;                  // row length / odd row pitch (floats)
+    // channels of this split that exist in dw (lddw < Cin: the input was stored with zero-padded channels, e.g. the 3-channel stem)
+    const int ci_w = max(0, min(ci_n, p.lddw - ci_lo));
+    const int RL = ci_w * g.taps, RLp = RL | 1;                  // row length / odd row pitch (floats)
     float* red = reinterpret_cast<float*>(Sbase);
     const int nch = (ci_n + 15) / 16;                            // 16-column chunks per tap
     if ((size_t)co_n * RLp * 4 <= (size_t)g.nstage * g.stage_bytes) {
@@ -332,13 +334,13 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
             tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * g.CI + c0), v);
             if (mine) {
               float* o = red + cr * RLp + c0 * g.taps + tap;
-              if (c0 + 16 <= ci_n) {
+              if (c0 + 16 <= ci_w) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) o[i * g.taps] = (pass == 0) ? v[i] : o[i * g.taps] + v[i];
               } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                  if (c0 + i < ci_n) o[i * g.taps] = (pass == 0) ? v[i] : o[i * g.taps] + v[i];
+                  if (c0 + i < ci_w) o[i * g.taps] = (pass == 0) ? v[i] : o[i * g.taps] + v[i];
               }
             }
           }
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int ci = ci_lo + c0 + i;
-            if (c0 + i < ci_n) atomicAdd(p.dw + ((long)co * p.lddw + ci) * g.taps + tap, v[i]);
+            if (c0 + i < ci_w) atomicAdd(p.dw + ((long)co * p.lddw + ci) * g.taps + tap, v[i]);
           }
         }
       }
@@ -385,7 +387,8 @@ int hcm_tc_wgrad_supported(int B, int H, int W, int Cin, int Cout, int ks, int s
 }
 
 // dw[Cout,Cin,ks,ks] += sum_pixels dy * T(x)   (fp32 atomics across CTAs; the caller zeroes dw once per step).
-// lddw > 0: dw is a column block of a wider [Cout][lddw][ks][ks] tensor
+// lddw > 0: dw is a column block of a wider [Cout][lddw][ks][ks] tensor; lddw < Cin: dw has only lddw input channels (x is stored
+// with zero-padded channels): the gradient of the padding channels is dropped
 int hcm_tc_wgrad(const float* x, const float* dy, float* dw, int lddw, int B, int H, int W, int Cin, int Cout, int ks, int stride,
                  const float* in_scale, const float* in_shift, int in_relu, cudaStream_t stream) {
   HCM_CHECK_ARG(x && dy && dw, "tc_wgrad: null pointer");

@@ -330,9 +330,17 @@ class Engine:
         # model
         xs = []
         for m in range(2):
-            xin = K.empty(B, R, R, 3)
-            p.f(K.nchw_to_nhwc, self.x, xin, B, 6, R * R, 3 * m, 3)
-            xs.append(Act(xin, B, R, R, 3, needs_grad=False))
+            if self.use_tc and K.tc_conv_supported(B, R, R, 4, 64, 3, 2) and K.tc_wgrad_supported(B, R, R, 4, 64, 3, 2):
+                # the 3-channel planes are stored with a zero 4th channel (16-byte rows, even channel count): the stem convolution
+                # and its weight gradient then run on the tensor-core kernels instead of the SIMT ones (B=64, 256^2:
+                # 489 + 805 us per encoder before); the weight keeps its [64,3,3,3] checkpoint layout (pack / wgrad with ld = 3)
+                xin = K.empty(B, R, R, 4)
+                p.f(K.nchw_to_nhwc_pad, self.x, xin, B, 6, R * R, 3 * m, 3, 4)
+                xs.append(Act(xin, B, R, R, 4, needs_grad=False))
+            else:
+                xin = K.empty(B, R, R, 3)
+                p.f(K.nchw_to_nhwc, self.x, xin, B, 6, R * R, 3 * m, 3)
+                xs.append(Act(xin, B, R, R, 3, needs_grad=False))
         p.fork(0, [1])
         self.feat1 = self._hrnet("encoder1.", xs[0])
         p.tag = 1
@@ -439,8 +447,10 @@ class Engine:
     # ---- conv + train-mode BN; output is lazy (raw conv output + per-channel affine)
     def _conv_bn(self, x, ck, bk, stride, relu):
         K, p, st = self.K, self.plan, self.store
-        cout, cin, ks, _ = st.keys[ck + ".weight"]
-        assert cin == x.C, (ck, cin, x.C)
+        cout, cin_w, ks, _ = st.keys[ck + ".weight"]
+        cin = x.C                              # channels of the stored input; > cin_w only for the zero-padded stem input (3 -> 4)
+        assert cin == cin_w or (cin == 4 and cin_w == 3 and not x.needs_grad), (ck, cin_w, x.C)
+        ldw = cin_w if cin != cin_w else 0
         B, H, W = x.B, x.H, x.W
         pad = (ks - 1) // 2
         Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
@@ -455,7 +465,7 @@ class Engine:
             nb = K.tc_conv_wpack_bytes(B, H, W, cin, cout, ks)
             wp_f = K.empty((nb + 3) // 4)
             rows = K.colstat_rows(P, cout)
-            self._pack_job(w, 0, wp_f, (B, H, W), cin, cout, ks, 4 * K.tc_conv_rowcat_supported(cout, ks, stride))
+            self._pack_job(w, ldw, wp_f, (B, H, W), cin, cout, ks, 4 * K.tc_conv_rowcat_supported(cout, ks, stride))
             assert rows * 2 * cout <= self.part.numel()
             p.f(K.tc_conv, x.data, wp_f, None, y, B, H, W, cin, cout, ks, stride, x.scale, x.shift, int(x.relu), 0)
             self._bn_stats(y, P, cout, bk, BN2D_MOMENTUM, scale, shift, mean, invstd)
@@ -481,7 +491,7 @@ class Engine:
                 spec["g_out"], spec["g_acc"], P, cout)
             dy = spec["dy"]
             if self.use_tc and K.tc_wgrad_supported(B, H, W, cin, cout, ks, stride):
-                p.b_off_path(K.tc_wgrad, x.data, dy, st.grad(ck + ".weight"), 0, B, H, W, cin, cout, ks, stride, x.scale, x.shift,
+                p.b_off_path(K.tc_wgrad, x.data, dy, st.grad(ck + ".weight"), ldw, B, H, W, cin, cout, ks, stride, x.scale, x.shift,
                              int(x.relu))
             else:
                 p.b_off_path(K.conv2d_wgrad, x.data, dy, st.grad(ck + ".weight"), B, H, W, cin, cout, ks, stride, x.scale,

@@ -120,6 +120,8 @@ int hcm_axpy(float* dst, const float* src, float alpha, long total, cudaStream_t
 /* ---- layout / resampling (resample.cu) : torch.split build_backbone.py:261; HR-module fuse
  *      official_hrnet.py:232-247; merge_all_res build_backbone.py:247-254; avg-pool :267-278 ---- */
 int hcm_nchw_to_nhwc(const float* x, float* out, int B, int Ctot, long HW, int coff, int Cn, cudaStream_t stream);
+int hcm_nchw_to_nhwc_pad(const float* x, float* out, int B, int Ctot, long HW, int coff, int Cn, int Cpad,
+                         cudaStream_t stream);   /* out [B,HW,Cpad], channels Cn..Cpad-1 zero */
 int hcm_fuse_sum(int nterms, const float* const* ptrs, const float* const* scales, const float* const* shifts,
                  const int* log2f, const float* bias, int relu, float* out, int B, int H, int W, int C,
                  cudaStream_t stream);

@@ -116,7 +116,10 @@ class TorchKernels:
         # the "packed" form of the reference is simply the effective OIHW weight of the GEMM being run
         O, I = (Cin, Cout) if transpose else (Cout, Cin)                         # dims of the OIHW slice
         ld = ldw if ldw > 0 else I
-        wv = torch.as_strided(w, (O, I, ks, ks), (ld * ks * ks, ks * ks, ks, 1), w.storage_offset())
+        Iv = min(I, ld) if not transpose else I                                  # forward, ldw < Cin: K zero-padded to Cin
+        wv = torch.as_strided(w, (O, Iv, ks, ks), (ld * ks * ks, ks * ks, ks, 1), w.storage_offset())
+        if Iv < I:
+            wv = torch.cat([wv, torch.zeros(O, I - Iv, ks, ks, dtype=w.dtype, device=w.device)], 1)
         if transpose:
             weff = wv.transpose(0, 1).flip(2, 3)                                 # w is [Cout(w)=Cin'][Cin(w)=Cout']
         else:
@@ -158,7 +161,8 @@ class TorchKernels:
         ld = lddw if lddw > 0 else Cin
         tmp = torch.zeros(Cout, Cin, ks, ks, dtype=dw.dtype, device=dw.device)
         self.conv2d_wgrad(x, dy, tmp, B, H, W, Cin, Cout, ks, stride, sc, sh, relu)
-        torch.as_strided(dw, (Cout, Cin, ks, ks), (ld * ks * ks, ks * ks, ks, 1), dw.storage_offset()).add_(tmp)
+        Cw = min(Cin, ld)                                                        # lddw < Cin: dw has only lddw input channels
+        torch.as_strided(dw, (Cout, Cw, ks, ks), (ld * ks * ks, ks * ks, ks, 1), dw.storage_offset()).add_(tmp[:, :Cw])
         return 0
 
     def gemm(self, A, Bm, bias, C, batch, M, N, K, sAm, sAk, sBk, sBn, sCm, bsA, bsB, bsC, alpha, accumulate):
@@ -278,6 +282,12 @@ class TorchKernels:
         return 0
 
     # ---------------------------------------------------------------- resample.cu
+    def nchw_to_nhwc_pad(self, x, out, B, Ctot, HW, coff, Cn, Cpad):
+        o = out.reshape(B, HW, Cpad)
+        o.zero_()
+        o[:, :, :Cn] = x.reshape(B, Ctot, HW)[:, coff:coff + Cn].permute(0, 2, 1)
+        return 0
+
     def nchw_to_nhwc(self, x, out, B, Ctot, HW, coff, Cn):
         v = x.reshape(B, Ctot, HW)[:, coff:coff + Cn].permute(0, 2, 1)
         out.reshape(B, HW, Cn).copy_(v)

@@ -600,3 +600,32 @@ def test_seg_head_kernels(KK, P):
     kc.seg_ce_fwd(logits, ign, cw, P, Cn, 255, acc, out2)
     kc.seg_ce_bwd(logits, ign, cw, P, Cn, 255, acc, 10.0, dl)
     assert float(out2[0]) == 0.0 and float(dl.abs().max()) == 0.0
+
+
+def test_padded_stem_conv_on_tensor_cores(KK):
+    """The 3-channel stem on the tensor-core kernels: input stored with a zero 4th channel (hcm_nchw_to_nhwc_pad), weights / weight
+    gradient in the [64,3,3,3] checkpoint layout (pack and wgrad with ld = 3 < Cin = 4)."""
+    kc, kr = KK
+    B, R, Cout = 3, 64, 64
+    x = rnd(B, 6, R, R)
+    w = rnd(Cout, 3, 3, 3, scale=0.2)
+    xin1, xin2 = torch.empty(B, R, R, 4, device=DEV), torch.empty(B, R, R, 4, device=DEV)
+    kc.nchw_to_nhwc_pad(x, xin1, B, 6, R * R, 3, 3, 4)
+    kr.nchw_to_nhwc_pad(x, xin2, B, 6, R * R, 3, 3, 4)
+    assert torch.equal(xin1, xin2) and float(xin1[..., 3].abs().max()) == 0.0
+    assert kc.tc_conv_supported(B, R, R, 4, Cout, 3, 2) and kc.tc_wgrad_supported(B, R, R, 4, Cout, 3, 2)
+    wp = torch.zeros((kc.tc_conv_wpack_bytes(B, R, R, 4, Cout, 3) + 3) // 4, device=DEV)
+    kc.tc_conv_pack(w, 3, wp, B, R, R, 4, Cout, 3, 0)
+    y1 = torch.empty(B, R // 2, R // 2, Cout, device=DEV)
+    kc.tc_conv(xin1, wp, None, y1, B, R, R, 4, Cout, 3, 2, None, None, 0, 0)
+    y2 = torch.nn.functional.conv2d(x[:, 3:6], w, None, 2, 1).permute(0, 2, 3, 1)
+    assert rel(y1, y2) < 3e-5, rel(y1, y2)
+    dy = rnd(B, R // 2, R // 2, Cout, seed=3)
+    dw1 = torch.zeros_like(w)
+    guard = dw1.clone()
+    kc.tc_wgrad(xin1, dy, dw1, 3, B, R, R, 4, Cout, 3, 2, None, None, 0)
+    xr = x[:, 3:6].clone().requires_grad_(False)
+    wr = w.clone().requires_grad_(True)
+    (torch.nn.functional.conv2d(xr, wr, None, 2, 1) * dy.permute(0, 3, 1, 2)).sum().backward()
+    assert rel(dw1, wr.grad) < 3e-5, rel(dw1, wr.grad)
+    del guard
