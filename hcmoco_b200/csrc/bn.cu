@@ -126,6 +126,8 @@ __global__ void colstat_kernel(const float* __restrict__ a, const float* __restr
                                const float* __restrict__ msc, const float* __restrict__ msh, long total, int C,
                                long per_cta, float* part, unsigned int* counter, double count, const Fin fin) {
   __shared__ float s0[MAXT * 4], s1[MAXT * 4];
+  pdl_wait();
+  pdl_trigger();                 // single-wave grid (<= 4 CTAs per SM): dependents may become resident right away
   const int t = threadIdx.x, nt = blockDim.x;
   const int cv = C / VEC;
   const int c0 = (t % cv) * VEC;
@@ -210,6 +212,8 @@ __device__ __forceinline__ void block_sum2_d(double& s, double& q, double* red) 
 __global__ void __launch_bounds__(128) bn_finalize_kernel(const float* __restrict__ part, int nparts, int C, double count,
                                                           const FwdFin f) {
   __shared__ double red[8];
+  pdl_wait();
+  pdl_trigger();
   const int c = blockIdx.x;
   if (blockIdx.x == 0 && threadIdx.x == 0 && f.nbt) *f.nbt += 1;
   double s = 0.0, q = 0.0;
@@ -225,6 +229,8 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const float* __restric
 __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, double count,
                                                               const BwdFin f) {
   __shared__ double red[8];
+  pdl_wait();
+  pdl_trigger();
   const int c = blockIdx.x;
   double s = 0.0, q = 0.0;
   for (int i = threadIdx.x; i < nparts; i += 128) {
@@ -240,6 +246,7 @@ template <int VEC>
 __global__ void bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                                 const float* __restrict__ res, const float* __restrict__ res_scale,
                                 const float* __restrict__ res_shift, int relu, float* __restrict__ out, long total, int C) {
+  pdl_wait();
   const int t = threadIdx.x, nt = blockDim.x;
   const int cv = C / VEC;
   const int c0 = (t % cv) * VEC;
@@ -267,6 +274,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, const float* __rest
     }
     vstore<VEC>(out + e, v);
   }
+  pdl_trigger();
 }
 
 // g = dz*[mask>0];  dy = k1*g + k2*y + k3;  optionally g_out (+)= g
@@ -275,6 +283,7 @@ __global__ void bn_bwd_apply_kernel(const float* dz, const float* __restrict__ m
                                     const float* __restrict__ msc, const float* __restrict__ msh,
                                     const float* __restrict__ k1, const float* __restrict__ k2, const float* __restrict__ k3,
                                     float* dy, float* g_out, int g_accumulate, long total, int C) {
+  pdl_wait();
   const int t = threadIdx.x, nt = blockDim.x;
   const int cv = C / VEC;
   const int c0 = (t % cv) * VEC;
@@ -311,6 +320,7 @@ __global__ void bn_bwd_apply_kernel(const float* dz, const float* __restrict__ m
       vstore<VEC>(g_out + e, g);
     }
   }
+  pdl_trigger();
 }
 
 // generic elementwise helpers (float4 main body + scalar tail)
@@ -355,9 +365,9 @@ int launch_colstat(const float* a, const float* y, const float* mask, const floa
   long per;
   const long total = P * C;
   colstat_plan(total, C, &vec, &threads, &nparts, &per);
-  if (vec == 4) colstat_kernel<4, MODE, Fin><<<nparts, threads, 0, stream>>>(a, y, mask, mean, invstd, msc, msh, total, C, per, part, counter, (double)P, fin);
-  else if (vec == 2) colstat_kernel<2, MODE, Fin><<<nparts, threads, 0, stream>>>(a, y, mask, mean, invstd, msc, msh, total, C, per, part, counter, (double)P, fin);
-  else colstat_kernel<1, MODE, Fin><<<nparts, threads, 0, stream>>>(a, y, mask, mean, invstd, msc, msh, total, C, per, part, counter, (double)P, fin);
+  if (vec == 4) hcm_launch_pdl(colstat_kernel<4, MODE, Fin>, nparts, threads, 0, stream, a, y, mask, mean, invstd, msc, msh, total, C, per, part, counter, (double)P, fin);
+  else if (vec == 2) hcm_launch_pdl(colstat_kernel<2, MODE, Fin>, nparts, threads, 0, stream, a, y, mask, mean, invstd, msc, msh, total, C, per, part, counter, (double)P, fin);
+  else hcm_launch_pdl(colstat_kernel<1, MODE, Fin>, nparts, threads, 0, stream, a, y, mask, mean, invstd, msc, msh, total, C, per, part, counter, (double)P, fin);
   return HCM_OK;
 }
 
@@ -385,7 +395,7 @@ int hcm_bn_finalize(const float* part, int nparts, int C, long count, const floa
                     float* scale, float* shift, float* mean, float* invstd, cudaStream_t stream) {
   HCM_CHECK_ARG(part && scale && shift && mean && invstd && nparts >= 1, "bn_finalize: bad args");
   const FwdFin f = {gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift, mean, invstd};
-  bn_finalize_kernel<<<C, 128, 0, stream>>>(part, nparts, C, (double)count, f);
+  hcm_launch_pdl(bn_finalize_kernel, C, 128, 0, stream, part, nparts, C, (double)count, f);
   HCM_LAUNCH_CHECK("bn_finalize");
   return HCM_OK;
 }
@@ -410,9 +420,9 @@ int hcm_bn_apply(const float* y, const float* scale, const float* shift, const f
   const long total = P * C;
   const int vec = vec_for(total, C), threads = threads_for(C, vec);
   const int grid = ew_grid(total, vec * 4, threads);
-  if (vec == 4) bn_apply_kernel<4><<<grid, threads, 0, stream>>>(y, scale, shift, res, res_scale, res_shift, relu, out, total, C);
-  else if (vec == 2) bn_apply_kernel<2><<<grid, threads, 0, stream>>>(y, scale, shift, res, res_scale, res_shift, relu, out, total, C);
-  else bn_apply_kernel<1><<<grid, threads, 0, stream>>>(y, scale, shift, res, res_scale, res_shift, relu, out, total, C);
+  if (vec == 4) hcm_launch_pdl(bn_apply_kernel<4>, grid, threads, 0, stream, y, scale, shift, res, res_scale, res_shift, relu, out, total, C);
+  else if (vec == 2) hcm_launch_pdl(bn_apply_kernel<2>, grid, threads, 0, stream, y, scale, shift, res, res_scale, res_shift, relu, out, total, C);
+  else hcm_launch_pdl(bn_apply_kernel<1>, grid, threads, 0, stream, y, scale, shift, res, res_scale, res_shift, relu, out, total, C);
   HCM_LAUNCH_CHECK("bn_apply");
   return HCM_OK;
 }
@@ -432,7 +442,7 @@ int hcm_bn_bwd_finalize(const float* part, int nparts, int C, long count, const 
                         cudaStream_t stream) {
   HCM_CHECK_ARG(part && mean && invstd && k1 && k2 && k3, "bn_bwd_finalize: bad args");
   const BwdFin f = {gamma, mean, invstd, dgamma, dbeta, k1, k2, k3};
-  bn_bwd_finalize_kernel<<<C, 128, 0, stream>>>(part, nparts, C, (double)count, f);
+  hcm_launch_pdl(bn_bwd_finalize_kernel, C, 128, 0, stream, part, nparts, C, (double)count, f);
   HCM_LAUNCH_CHECK("bn_bwd_finalize");
   return HCM_OK;
 }
@@ -457,9 +467,9 @@ int hcm_bn_bwd_apply(const float* dz, const float* mask, const float* mask_scale
   const long total = P * C;
   const int vec = vec_for(total, C), threads = threads_for(C, vec);
   const int grid = ew_grid(total, vec * 4, threads);
-  if (vec == 4) bn_bwd_apply_kernel<4><<<grid, threads, 0, stream>>>(dz, mask, y, mask_scale, mask_shift, k1, k2, k3, dy, g_out, g_accumulate, total, C);
-  else if (vec == 2) bn_bwd_apply_kernel<2><<<grid, threads, 0, stream>>>(dz, mask, y, mask_scale, mask_shift, k1, k2, k3, dy, g_out, g_accumulate, total, C);
-  else bn_bwd_apply_kernel<1><<<grid, threads, 0, stream>>>(dz, mask, y, mask_scale, mask_shift, k1, k2, k3, dy, g_out, g_accumulate, total, C);
+  if (vec == 4) hcm_launch_pdl(bn_bwd_apply_kernel<4>, grid, threads, 0, stream, dz, mask, y, mask_scale, mask_shift, k1, k2, k3, dy, g_out, g_accumulate, total, C);
+  else if (vec == 2) hcm_launch_pdl(bn_bwd_apply_kernel<2>, grid, threads, 0, stream, dz, mask, y, mask_scale, mask_shift, k1, k2, k3, dy, g_out, g_accumulate, total, C);
+  else hcm_launch_pdl(bn_bwd_apply_kernel<1>, grid, threads, 0, stream, dz, mask, y, mask_scale, mask_shift, k1, k2, k3, dy, g_out, g_accumulate, total, C);
   HCM_LAUNCH_CHECK("bn_bwd_apply");
   return HCM_OK;
 }

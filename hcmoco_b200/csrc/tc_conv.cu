@@ -378,15 +378,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
     for (int i = threadIdx.x; i < g.nsteps; i += NTHREADS)
       s_steps[i] = make_uint2(p.steps[i].x >> 4, b_lo32 + ((w0s + p.steps[i].y * (uint32_t)g.wslab) >> 4));
   }
-  for (int c = threadIdx.x; c < 256; c += NTHREADS) {
-    s_sc[c] = (p.in_scale && c < p.Cin) ? p.in_scale[c] : 1.f;
-    s_sh[c] = (p.in_scale && c < p.Cin) ? p.in_shift[c] : 0.f;
-  }
   // zero the staged A buffers once: K-padding channels are never written afterwards and must read as 0
   for (size_t i = threadIdx.x; i < (size_t)g.nastage * g.a_stage_bytes / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(Abase)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   if (warp == W_MMA) tmem_alloc(smem_u32(tmem_ptr), g.tmem_cols);
+  // everything above touched only shared memory / TMEM / kernel parameters: with a programmatic dependent launch it ran while the
+  // stream predecessor was still finishing.  From here on the predecessor's results are read (common.cuh: PDL protocol).
+  pdl_wait();
+  pdl_trigger();
+  for (int c = threadIdx.x; c < 256; c += NTHREADS) {
+    s_sc[c] = (p.in_scale && c < p.Cin) ? p.in_scale[c] : 1.f;
+    s_sh[c] = (p.in_scale && c < p.Cin) ? p.in_shift[c] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -876,7 +880,7 @@ int launch_tc(TcParams& p, cudaStream_t stream, const char* what) {
     if (e != cudaSuccess) { hcm_set_error("%s: smem attribute: %s", what, cudaGetErrorString(e)); return HCM_ERR_CUDA; }
     configured = true;
   }
-  tc_conv_kernel<<<(unsigned)p.g.grid, NTHREADS, p.g.smem, stream>>>(p);
+  hcm_launch_pdl(tc_conv_kernel, dim3((unsigned)p.g.grid), dim3(NTHREADS), p.g.smem, stream, p);
   HCM_LAUNCH_CHECK(what);
   if (dbg_on) {
     long long h[148 * 16];

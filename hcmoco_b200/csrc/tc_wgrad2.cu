@@ -164,15 +164,17 @@ __global__ void __launch_bounds__(NTHREADS_W, 1) tc_wgrad2_kernel(const WParams 
     mbar_init(BAR(8), 1);
     fence_mbar_init();
   }
-  for (int c = threadIdx.x; c < 256; c += NTHREADS_W) {
-    s_sc[c] = (p.in_scale && c < p.Cin) ? p.in_scale[c] : 1.f;
-    s_sh[c] = (p.in_scale && c < p.Cin) ? p.in_shift[c] : 0.f;
-  }
   // zero all staged tiles once (channel padding is never written afterwards and must read as 0)
   for (size_t i = threadIdx.x; i < ((size_t)g.nstage * g.stage_bytes) / 16; i += NTHREADS_W)
     reinterpret_cast<uint4*>(Sbase)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   if (warp == W_MMA) tmem_alloc(smem_u32(tmem_ptr), g.tmem_cols);
+  pdl_wait();                    // (PDL protocol, common.cuh: only shared memory / TMEM / parameters were touched so far)
+  pdl_trigger();
+  for (int c = threadIdx.x; c < 256; c += NTHREADS_W) {
+    s_sc[c] = (p.in_scale && c < p.Cin) ? p.in_scale[c] : 1.f;
+    s_sh[c] = (p.in_scale && c < p.Cin) ? p.in_shift[c] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -413,7 +415,7 @@ int hcm_tc_wgrad(const float* x, const float* dy, float* dw, int lddw, int B, in
   }
   p.dbg = dbg;
   dim3 grid(p.g.ntr, p.g.nsplit, p.g.nblk);
-  tc_wgrad2_kernel<<<grid, NTHREADS_W, p.g.smem, stream>>>(p);
+  hcm_launch_pdl(tc_wgrad2_kernel, grid, dim3(NTHREADS_W), p.g.smem, stream, p);
   HCM_LAUNCH_CHECK("tc_wgrad");
   if (dbg_on) {
     long long h[8];
