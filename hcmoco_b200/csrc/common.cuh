@@ -65,6 +65,24 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 
+// Division of 0 <= n < 2^31 by a launch constant without the ~40-instruction emulated integer divide (the position decode of
+// every staged row and, worse, the per-tile bookkeeping of the single MMA-issuing warp): m = ceil(2^(31+l) / d), l = ceil(log2 d),
+// n / d = umulhi(n, m) >> (l - 1)  (error term n / 2^(31+l) < 2^-l <= 1/d, so the floor is exact).
+struct FastDiv { uint32_t d, m, s; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f; f.d = d; f.m = 0; f.s = 0;
+  if (d <= 1) return f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  const unsigned long long k = 31 + l, p2 = 1ull << k;
+  f.m = (uint32_t)((p2 + d - 1) / d);
+  f.s = l - 1;
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return f.d <= 1 ? n : (__umulhi(n, f.m) >> f.s); }
+#endif
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

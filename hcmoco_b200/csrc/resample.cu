@@ -28,49 +28,71 @@ struct FuseParams {
 
 // PyTorch upsample_bilinear2d, align_corners=False, scale = in/out = 1/f
 __device__ __forceinline__ void src_index(int dst, int f, int in_size, int& i0, int& i1, float& l1) {
-  float s = ((float)dst + 0.5f) / (float)f - 0.5f;
+  float s = ((float)dst + 0.5f) * (1.f / (float)f) - 0.5f;      // f is a power of two: the reciprocal and the product are exact
   if (s < 0.f) s = 0.f;
   i0 = (int)s;
   i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
   l1 = s - (float)i0;
 }
 
-__global__ void fuse_sum_kernel(const FuseParams p) {
-  const long total = (long)p.B * p.H * p.W * p.C;
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-    const int c = (int)(e % p.C);
-    long pix = e / p.C;
-    const int w = (int)(pix % p.W);
-    pix /= p.W;
-    const int h = (int)(pix % p.H);
-    const int b = (int)(pix / p.H);
-    float acc = p.bias ? p.bias[c] : 0.f;
+// One thread per (pixel, V channels): 32-bit index arithmetic with multiply-high divisions (the first version decoded every ELEMENT
+// with six emulated 64-bit divisions: 52 us per launch in the step for a 19 MB output), the bilinear source rows / weights computed
+// once per pixel and term, 8-byte loads and stores when C is even.  The per-element arithmetic (and its order) is unchanged.
+template <int V>
+__global__ void fuse_sum_kernel(const FuseParams p, FastDiv fd_cv, FastDiv fd_w, FastDiv fd_h, unsigned items) {
+  const unsigned cv = (unsigned)p.C / V;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += stride) {
+    const unsigned pix = fdiv(it, fd_cv), c = (it - pix * cv) * V;
+    const unsigned t2 = fdiv(pix, fd_w), w = pix - t2 * (unsigned)p.W;
+    const unsigned b = fdiv(t2, fd_h), h = t2 - b * (unsigned)p.H;
+    const size_t e = (size_t)pix * p.C + c;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = p.bias ? p.bias[c + i] : 0.f;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       if (t >= p.nterms) break;
       const FuseTerm& T = p.t[t];
-      float v;
+      float v[V];
       if (T.log2f == 0) {
-        v = T.ptr[e];
+        if (V == 2) { const float2 a = *reinterpret_cast<const float2*>(T.ptr + e); v[0] = a.x; v[V - 1] = a.y; }
+        else v[0] = T.ptr[e];
       } else {
         const int f = 1 << T.log2f;
         const int Hs = p.H >> T.log2f, Ws = p.W >> T.log2f;
         int y0, y1, x0, x1;
         float ly, lx;
-        src_index(h, f, Hs, y0, y1, ly);
-        src_index(w, f, Ws, x0, x1, lx);
-        const float* base = T.ptr + (long)b * Hs * Ws * p.C + c;
-        const float v00 = base[((long)y0 * Ws + x0) * p.C], v01 = base[((long)y0 * Ws + x1) * p.C];
-        const float v10 = base[((long)y1 * Ws + x0) * p.C], v11 = base[((long)y1 * Ws + x1) * p.C];
+        src_index((int)h, f, Hs, y0, y1, ly);
+        src_index((int)w, f, Ws, x0, x1, lx);
+        const float* base = T.ptr + (size_t)b * Hs * Ws * p.C + c;
+        const float* q00 = base + ((size_t)y0 * Ws + x0) * p.C;
+        const float* q01 = base + ((size_t)y0 * Ws + x1) * p.C;
+        const float* q10 = base + ((size_t)y1 * Ws + x0) * p.C;
+        const float* q11 = base + ((size_t)y1 * Ws + x1) * p.C;
+        float v00[V], v01[V], v10[V], v11[V];
+        if (V == 2) {
+          const float2 a = *reinterpret_cast<const float2*>(q00), bq = *reinterpret_cast<const float2*>(q01);
+          const float2 cq = *reinterpret_cast<const float2*>(q10), d = *reinterpret_cast<const float2*>(q11);
+          v00[0] = a.x; v00[V - 1] = a.y; v01[0] = bq.x; v01[V - 1] = bq.y;
+          v10[0] = cq.x; v10[V - 1] = cq.y; v11[0] = d.x; v11[V - 1] = d.y;
+        } else { v00[0] = *q00; v01[0] = *q01; v10[0] = *q10; v11[0] = *q11; }
         const float hy = 1.f - ly, hx = 1.f - lx;
-        v = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[i] = hy * (hx * v00[i] + lx * v01[i]) + ly * (hx * v10[i] + lx * v11[i]);
       }
-      if (T.scale) v = fmaf(v, T.scale[c], T.shift ? T.shift[c] : 0.f);
-      acc += v;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        if (T.scale) v[i] = fmaf(v[i], T.scale[c + i], T.shift ? T.shift[c + i] : 0.f);
+        acc[i] += v[i];
+      }
     }
-    if (p.relu) acc = fmaxf(acc, 0.f);
-    p.out[e] = acc;
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = fmaxf(acc[i], 0.f);
+    }
+    if (V == 2) *reinterpret_cast<float2*>(p.out + e) = make_float2(acc[0], acc[V - 1]);
+    else p.out[e] = acc[0];
   }
 }
 
@@ -126,25 +148,37 @@ __global__ void upsample_adjoint_kernel(const float* __restrict__ g, float* out,
 __global__ void upsample_adjoint_rows_kernel(const float* __restrict__ g, float* out, int accumulate, int B, int H, int W, int C,
                                              int log2f) {
   extern __shared__ float tmp[];
-  const int f = 1 << log2f;
+  const int f = 1 << log2f, f2 = 2 * f;
   const int Hs = H >> log2f, Ws = W >> log2f;
   const int b = blockIdx.x / Hs, Y = blockIdx.x - b * Hs;
   const int hlo = max(0, f * Y - f / 2), hhi = min(H - 1, f * Y + f + f / 2 - 1);
   const int R = hhi - hlo + 1, WC = Ws * C;
+  // tap weights once per CTA (they were recomputed, with a float division each, for every element and tap):
+  // wxt[X][j] = weight of high-res column wlo(X) + j towards X (0 past the last contributing column), wyt[r] likewise for rows
+  float* wxt = tmp + (size_t)f2 * WC;
+  float* wyt = wxt + Ws * f2;
+  for (int e = threadIdx.x; e < Ws * f2; e += blockDim.x) {
+    const int X = e / f2, j = e - X * f2;
+    const int wlo = max(0, f * X - f / 2), whi = min(W - 1, f * X + f + f / 2 - 1);
+    wxt[e] = (wlo + j <= whi) ? adj_weight(wlo + j, log2f, Ws, X) : 0.f;
+  }
+  for (int r = threadIdx.x; r < f2; r += blockDim.x) wyt[r] = (r < R) ? adj_weight(hlo + r, log2f, Hs, Y) : 0.f;
+  __syncthreads();
   for (int e = threadIdx.x; e < R * WC; e += blockDim.x) {
     const int r = e / WC, xc = e - r * WC;
     const int X = xc / C, c = xc - X * C;
     const int wlo = max(0, f * X - f / 2), whi = min(W - 1, f * X + f + f / 2 - 1);
     const float* row = g + ((long)(b * H + hlo + r) * W) * C + c;
+    const float* wt = wxt + X * f2;
     float acc = 0.f;
-    for (int w = wlo; w <= whi; ++w) acc = fmaf(adj_weight(w, log2f, Ws, X), __ldg(row + (long)w * C), acc);
+    for (int w = wlo; w <= whi; ++w) acc = fmaf(wt[w - wlo], __ldg(row + (long)w * C), acc);
     tmp[e] = acc;
   }
   __syncthreads();
   float* orow = out + ((long)(b * Hs + Y) * Ws) * C;
   for (int e = threadIdx.x; e < WC; e += blockDim.x) {
     float acc = 0.f;
-    for (int r = 0; r < R; ++r) acc = fmaf(adj_weight(hlo + r, log2f, Hs, Y), tmp[r * WC + e], acc);
+    for (int r = 0; r < R; ++r) acc = fmaf(wyt[r], tmp[r * WC + e], acc);
     orow[e] = accumulate ? orow[e] + acc : acc;
   }
 }
@@ -234,7 +268,12 @@ int hcm_fuse_sum(int nterms, const float* const* ptrs, const float* const* scale
     p.t[i].log2f = log2f[i];
   }
   p.nterms = nterms; p.bias = bias; p.relu = relu; p.out = out; p.B = B; p.H = H; p.W = W; p.C = C;
-  fuse_sum_kernel<<<ew_grid((long)B * H * W * C), 256, 0, stream>>>(p);
+  HCM_CHECK_ARG((long)B * H * W * C < (1L << 31), "fuse_sum: tensor too large for 32-bit indexing");
+  const int V = (C % 2 == 0) ? 2 : 1;
+  const unsigned items = (unsigned)((long)B * H * W * (C / V));
+  const FastDiv fd_cv = make_fastdiv((unsigned)(C / V)), fd_w = make_fastdiv((unsigned)W), fd_h = make_fastdiv((unsigned)H);
+  if (V == 2) fuse_sum_kernel<2><<<ew_grid((long)items * 4), 256, 0, stream>>>(p, fd_cv, fd_w, fd_h, items);
+  else fuse_sum_kernel<1><<<ew_grid((long)items * 4), 256, 0, stream>>>(p, fd_cv, fd_w, fd_h, items);
   HCM_LAUNCH_CHECK("fuse_sum");
   return HCM_OK;
 }
@@ -243,7 +282,7 @@ int hcm_fuse_sum(int nterms, const float* const* ptrs, const float* const* scale
 int hcm_upsample_adjoint(const float* g, float* out, int accumulate, int B, int H, int W, int C, int log2f,
                          cudaStream_t stream) {
   HCM_CHECK_ARG(g && out && log2f >= 1, "upsample_adjoint: bad args");
-  const size_t smem = (size_t)(2 << log2f) * (size_t)(W >> log2f) * C * sizeof(float);
+  const size_t smem = ((size_t)(2 << log2f) * (size_t)(W >> log2f) * C + (size_t)(2 << log2f) * ((W >> log2f) + 1)) * sizeof(float);
   if (smem <= 96 * 1024 && (H >> log2f) >= 1 && (W >> log2f) >= 1) {
     static bool attr = false;
     if (!attr) {
