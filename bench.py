@@ -517,6 +517,13 @@ def run_engine(a):
     ex = extra_configs(a, K, world, rank, dist)
     if ex:
         out["extra_configs"] = ex
+    if not a.no_extra and world == 1 and (a.stage, a.width, a.res, a.batch) == (1, 18, 256, 64):
+        try:
+            out["widened_rows"] = widened_rows(a, K, hbm_peak)
+        except Exception as ex_:
+            out["widened_rows"] = {"error": repr(ex_)[:300]}
+            gc.collect()
+            torch.cuda.empty_cache()
     if not a.no_gpu_eager and world == 1:
         eager = {}
         for name, tf32 in (("tf32_on", True), ("tf32_off", False)):
@@ -539,6 +546,86 @@ def run_engine(a):
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _median_ms(fn, reps=7):
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def widened_rows(a, K, hbm_peak):
+    """Measured numbers for the SURVEY.md section 8(f) rows built beside the pre-train path: input staging of
+    decoded frames (f1), the segmentation fine-tuning step (f3), farthest point sampling of the PointNet++ primitives (f4)."""
+    from types import SimpleNamespace
+    from hcmoco_b200.synthetic import make_batch
+    out = {}
+    g = torch.Generator().manual_seed(0)
+    # f1: B=64 NTU-sized frames (424 x 512 uint8 RGB + uint16 depth) -> x [64,6,256,256] + depth_mask
+    B, Hs, Ws, R = 64, 424, 512, 256
+    rgb = torch.randint(0, 256, (B, Hs, Ws, 3), generator=g, dtype=torch.uint8).cuda()
+    depth = torch.randint(500, 4000, (B, Hs, Ws), generator=g, dtype=torch.int32).to(torch.uint16).cuda()
+    crop = torch.tensor([[20, 40, 380, 380]] * B, dtype=torch.int32).cuda()
+    flip = torch.zeros(B, dtype=torch.int32).cuda()
+    sums, x, mask = torch.zeros(B, 2, dtype=torch.int64).cuda(), torch.empty(B, 6, R, R).cuda(), torch.empty(B, R, R).cuda()
+    K.stage_input(rgb, depth, crop, flip, None, B, Hs, Ws, R, sums, x, mask)
+    ms = _median_ms(lambda: K.stage_input(rgb, depth, crop, flip, None, B, Hs, Ws, R, sums, x, mask))
+    nbytes = B * (380 * 380 * 5 + 7 * R * R * 4)             # the crop window's uint8 x3 + uint16, the 6 + 1 fp32 output planes
+    out["f1_stage_input"] = {"ms": ms, "triplets_per_s": B / (ms * 1e-3), "achieved_GBps": nbytes / (ms * 1e-3) / 1e9,
+                             "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                             "shape": "B=64, 424x512 frames, 380x380 crop -> 256x256 (2 launches)"}
+    del rgb, depth, x, mask
+    # f3: the fused segmentation fine-tuning step, second-stage model, B=32, every sample labelled, 25 classes
+    from hcmoco_b200.api import HCMoCoMem, HCMoCoModel
+    from hcmoco_b200.segment import FCNHead, NTU_CLASS_WEIGHTS, SegTrainer
+    Bs = 32
+    opt = SimpleNamespace(modal="RGBD2S", arch="HRNet", jigsaw=False, head="linear", pool_method="mean", width=18, linear_feat_map=1,
+                          skeleton_meta_name="mpii", in_channel_list=[3, 3], feat_dim=128, mem="bank+jointspri3d", nce_k=a.nce_k,
+                          nce_t=0.07, nce_m=0.5, temperature=0.07, pri3d_num_samples_per_image=400, modality_missing=1,
+                          supervise_type=0, cmc_loss_weights=1, other_loss_weights=1, print_freq=1000, n_class=25, cuda_graph=True)
+    model = HCMoCoModel(opt, K)
+    mem = HCMoCoMem(128, a.n_data, a.nce_k, 0.07, 0.5, K)
+    clf = FCNHead(128, 128, 25, 1, 1, K, NTU_CLASS_WEIGHTS)
+    tr = SegTrainer(opt)
+    model.attach_memory(mem)
+    d = [t.cuda() for t in make_batch(Bs, R, 16, a.n_data, seed=5)]
+    label = torch.randint(0, 25, (Bs, R, R), generator=g).cuda()
+    data = list(d) + [None] * (11 - len(d))
+    data[9], data[10] = label, torch.ones(Bs, dtype=torch.int64).cuda()
+    for _ in range(3):
+        r = tr.seg_step(model, clf, mem, data, 0.03, 0.9, 1e-4)
+    torch.cuda.synchronize()
+    n = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        r = tr.seg_step(model, clf, mem, data, 0.03, 0.9, 1e-4)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    res = r()
+    out["f3_seg_step"] = {"ms_per_step": ms, "triplets_per_s": Bs / (ms * 1e-3), "seg_loss": float(res["seg_loss"]),
+                          "workload": "SegTrainer.seg_step: stage2 HRNet-w18+SemGCN, 256x256, batch 32 (all labelled), 25 classes; "
+                                      "engine programs as three CUDA graphs + the FCN head launched eagerly"}
+    del model, mem, clf, tr
+    gc.collect()
+    torch.cuda.empty_cache()
+    # f4: farthest point sampling at the Pointnet2MSG sizes (first two set-abstraction levels)
+    xyz = torch.randn(Bs, 4096, 3, generator=g).cuda()
+    fps = {}
+    for M in (4096, 1024):
+        idx = torch.zeros(Bs, M, dtype=torch.int32).cuda()
+        K.pn2_furthest_point_sampling(xyz, Bs, 4096, M, idx)
+        fps["M=%d" % M] = _median_ms(lambda: K.pn2_furthest_point_sampling(xyz, Bs, 4096, M, idx), 3)
+    out["f4_fps_ms"] = dict(fps, shape="B=32 clouds of 4096 points")
+    return out
 
 
 def extra_configs(a, K, world, rank, dist):

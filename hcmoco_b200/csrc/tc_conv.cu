@@ -362,12 +362,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv_kernel(const TcParams p) 
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < MAX_ASTAGE; ++s) { mbar_init(BAR(s), NTRANS / g.nastage); mbar_init(BAR(4 + s), 1); }
-    mbar_init(BAR(8), 1); mbar_init(BAR(9), 1);
-    mbar_init(BAR(10), 128); mbar_init(BAR(11), 128);
-    mbar_init(BAR(12), 1);
-    for (int s = 0; s < 16; ++s) { mbar_init(BAR(16 + s), 1); mbar_init(BAR(32 + s), 1); }
+  if (threadIdx.x < 48) {
+    // one barrier per thread (a single thread initialising all 45 serialised ~0.5 us into the prologue of every launch)
+    const int i = threadIdx.x;
+    const uint32_t count = i < 4 ? (uint32_t)(NTRANS / g.nastage) : ((i == 10 || i == 11) ? 128u : 1u);
+    if (i < 13 || i >= 16) mbar_init(BAR(i), count);
     fence_mbar_init();
   }
   {
