@@ -314,13 +314,24 @@ class Runner:
             ms = float(t)
         return ms
 
+    def _diag(self, what):
+        if self.world > 1 and os.environ.get("HCM_BENCH_DIAG"):
+            ok = replicas_identical(self.step, self.dist, self.world)
+            if int(os.environ.get("RANK", "0")) == 0:
+                sys.stderr.write("[diag] %-28s identical=%s %s\n" % (what, ok, replicas_identical.detail))
+
     def measure(self, steps, warmup):
         a = self.a
+        self._diag("after construction")
         for i in range(warmup):
             self.step.run(self.dev[i % 2])
+        self._diag("after warm-up")
         ms_dev = self.timed(self.dev, steps, False)
+        self._diag("after device-timed steps")
         self.step.run(self.host[0], next_batch=self.host[0])       # e2e warm-up: stager buffers, pinned result slots
+        self._diag("after e2e warm-up step")
         ms_e2e = self.timed(self.host, steps, True)
+        self._diag("after e2e steps")
         h2d = self.step.h2d_bytes(self.host[0])
         return {"value": a.batch * self.world * steps / (ms_dev / 1e3), "ms_per_step": ms_dev / steps,
                 "e2e": {"value": a.batch * self.world * steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -344,7 +355,20 @@ def replicas_identical(step, dist, world):
     mine = torch.stack(sums)
     allv = torch.empty(world, mine.numel(), dtype=torch.int64, device="cuda")
     dist.all_gather_into_tensor(allv, mine)
-    return bool((allv == allv[0:1]).all())
+    same = (allv == allv[0:1]).all(0).reshape(5, 2).all(1).tolist()
+    detail = dict(zip(("params", "momentum", "memory_1", "memory_2", "memory_3"), same))
+    # how far apart (and whether the training state is still finite): max |p - p(rank 0)| over the ranks
+    ref = e.store.p.clone()
+    dist.broadcast(ref, 0)
+    d = torch.stack([(e.store.p - ref).abs().max().nan_to_num(nan=-1.0), (~torch.isfinite(e.store.p)).sum().float(),
+                     e.store.p.abs().max().nan_to_num(nan=-1.0)])
+    alld = torch.empty(world, 3, device="cuda")
+    dist.all_gather_into_tensor(alld, d)
+    detail["params_max_abs_diff_vs_rank0"] = float(alld[:, 0].max())
+    detail["params_nonfinite"] = int(alld[:, 1].max())
+    detail["params_max_abs"] = float(alld[:, 2].max())
+    replicas_identical.detail = detail
+    return bool(all(same))
 
 
 def run_engine(a):
@@ -512,6 +536,7 @@ def run_engine(a):
            "kernel_families_calls": {k: v["calls"] for k, v in fam.items()}}
     if identical is not None:
         out["replicas_identical"] = identical
+        out["replicas_identical_detail"] = getattr(replicas_identical, "detail", None)
     run.close()
     step = run = None
     ex = extra_configs(a, K, world, rank, dist)

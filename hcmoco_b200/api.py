@@ -565,10 +565,11 @@ class ContrastTrainer(object):
             eng.forward()
             eng.backward()
         if world > 1:
-            h = dist.all_reduce(eng.store.g, async_op=True)
+            # synchronous collectives, one at a time (see pretrain.PretrainStep.run: an async all-reduce racing the gathers made
+            # the replicas drift on 8 GPUs)
             all_f, all_y = self._global_gather(eng.f), self._global_gather(eng.index)
+            dist.all_reduce(eng.store.g)
             eng.update_banks(all_f, all_y)
-            h.wait()
         else:
             eng.update_banks()
         optimizer.step(gscale=1.0 / world, from_autograd=False)

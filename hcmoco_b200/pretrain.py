@@ -179,11 +179,17 @@ class PretrainStep:
             e.backward()
         if self.world > 1:
             import torch.distributed as dist
-            h = dist.all_reduce(e.store.g, async_op=True)
+            # Two collectives of one communicator must never be in flight on different streams.  The first version issued the async
+            # all-reduce first and the synchronous all-gathers after it: the all-gathers could run on the compute stream while the
+            # all-reduce was still executing on the process group's stream — measured on 8 GPUs, the replicas' parameters drifted
+            # apart (max |dp| 0.03 after 24 steps; 2 and 4 GPUs were unaffected) although every call "completed" on every rank
+            # (bench.py `replicas_identical`, profiles/r02_bench_8gpu.json).
+            # All three are issued synchronously (one at a time whatever stream the process group uses for them); what the async
+            # variant overlapped with the all-reduce was three tiny bank-update kernels.
             dist.all_gather_into_tensor(self.all_f, e.f)
             dist.all_gather_into_tensor(self.all_y, e.index)
+            dist.all_reduce(e.store.g)
             e.update_banks(self.all_f, self.all_y)
-            h.wait()
             e.sgd(self.lr, self.momentum, self.wd, 1.0 / self.world)
         else:
             e.update_banks()

@@ -341,12 +341,11 @@ class SegTrainer(ContrastTrainer):
         else:
             eng.plan.run(eng.plan.bwd[eng.n_loss_bwd:], eng.two_streams)
         if world > 1:
-            h1 = dist.all_reduce(eng.store.g, async_op=True)
-            h2 = dist.all_reduce(head.store.g, async_op=True)
+            # synchronous collectives, one at a time (see pretrain.PretrainStep.run)
             all_f, all_y = self._global_gather(eng.f), self._global_gather(eng.index)
+            dist.all_reduce(eng.store.g)
+            dist.all_reduce(head.store.g)
             eng.update_banks(all_f, all_y)
-            h1.wait()
-            h2.wait()
         else:
             eng.update_banks()
         eng.sgd(lr, momentum, wd, 1.0 / world)
