@@ -36,136 +36,97 @@ def _i32(K, *shape):
     return torch.zeros(*shape, dtype=torch.int32, device=K.device)
 
 
-class FurthestPointSampling(Function):
-    @staticmethod
-    def forward(ctx, xyz, npoint):
-        assert xyz.is_contiguous()
-        K = _kernels()
-        B, N, _ = xyz.size()
-        out = _i32(K, B, npoint)
-        K.pn2_furthest_point_sampling(xyz, B, N, npoint, out)
-        return out
-
-    @staticmethod
-    def backward(ctx, a=None):
-        return None, None
+# ---- index producers (no gradient): plain functions
+@torch.no_grad()
+def furthest_point_sample(xyz, npoint):
+    """xyz [B,N,3] contiguous -> int32 [B,npoint]: iterative farthest point sampling from point 0 (pointnet2_utils.py:12-29)."""
+    assert xyz.is_contiguous()
+    K, (B, N, _) = _kernels(), xyz.shape
+    out = _i32(K, B, npoint)
+    K.pn2_furthest_point_sampling(xyz, B, N, npoint, out)
+    return out
 
 
-furthest_point_sample = FurthestPointSampling.apply
+@torch.no_grad()
+def three_nn(unknown, known):
+    """unknown [B,n,3], known [B,m,3] -> (distances [B,n,3] (square roots), int32 indices [B,n,3]) (pointnet2_utils.py:79-99)."""
+    assert unknown.is_contiguous() and known.is_contiguous()
+    K, (B, n, _), m = _kernels(), unknown.shape, known.shape[1]
+    d2, idx = torch.empty_like(unknown), _i32(K, B, n, 3)
+    K.pn2_three_nn(unknown, known, B, n, m, d2, idx)
+    return d2.sqrt_(), idx
 
 
-class GatherOperation(Function):
+@torch.no_grad()
+def ball_query(radius, nsample, xyz, new_xyz):
+    """int32 [B,npoint,nsample]: the first nsample points of xyz within `radius` of each new_xyz (pointnet2_utils.py:203-221)."""
+    assert new_xyz.is_contiguous() and xyz.is_contiguous()
+    K, (B, N, _), npoint = _kernels(), xyz.shape, new_xyz.shape[1]
+    idx = _i32(K, B, npoint, nsample)
+    K.pn2_ball_query(new_xyz, xyz, B, N, npoint, float(radius), int(nsample), idx)
+    return idx
+
+
+# ---- differentiable gathers: features [B,C,N] indexed along the point axis; the backward scatters into a zeroed buffer
+class _Gather(Function):
+    """gather_operation (idx [B,npoint]) and grouping_operation (idx [B,npoint,nsample]) are the same kernel family."""
+
     @staticmethod
     def forward(ctx, features, idx):
         assert features.is_contiguous() and idx.is_contiguous()
-        K = _kernels()
-        B, npoint = idx.size()
-        _, C, N = features.size()
-        out = torch.empty(B, C, npoint, dtype=features.dtype, device=features.device)
-        K.pn2_gather_points(features, idx, B, C, N, npoint, out)
-        ctx.for_backwards = (idx, C, N)
+        K, (B, C, N) = _kernels(), features.shape
+        out = features.new_empty((B, C) + tuple(idx.shape[1:]))
+        if idx.dim() == 2:
+            K.pn2_gather_points(features, idx, B, C, N, idx.shape[1], out)
+        else:
+            K.pn2_group_points(features, idx, B, C, N, idx.shape[1], idx.shape[2], out)
+        ctx.idx, ctx.N = idx, N
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        idx, C, N = ctx.for_backwards
-        K = _kernels()
-        B, npoint = idx.size()
-        grad = torch.zeros(B, C, N, dtype=grad_out.dtype, device=grad_out.device)
-        K.pn2_gather_points_grad(grad_out.contiguous(), idx, B, C, N, npoint, grad)
+        K, idx = _kernels(), ctx.idx
+        B, C = grad_out.shape[:2]
+        grad = grad_out.new_zeros(B, C, ctx.N)
+        g = grad_out.contiguous()
+        if idx.dim() == 2:
+            K.pn2_gather_points_grad(g, idx, B, C, ctx.N, idx.shape[1], grad)
+        else:
+            K.pn2_group_points_grad(g, idx, B, C, ctx.N, idx.shape[1], idx.shape[2], grad)
         return grad, None
 
 
-gather_operation = GatherOperation.apply
+def gather_operation(features, idx):
+    return _Gather.apply(features, idx)
 
 
-class ThreeNN(Function):
-    @staticmethod
-    def forward(ctx, unknown, known):
-        assert unknown.is_contiguous() and known.is_contiguous()
-        K = _kernels()
-        B, N, _ = unknown.size()
-        m = known.size(1)
-        dist2 = torch.empty(B, N, 3, dtype=unknown.dtype, device=unknown.device)
-        idx = _i32(K, B, N, 3)
-        K.pn2_three_nn(unknown, known, B, N, m, dist2, idx)
-        return torch.sqrt(dist2), idx
-
-    @staticmethod
-    def backward(ctx, a=None, b=None):
-        return None, None
+def grouping_operation(features, idx):
+    return _Gather.apply(features, idx)
 
 
-three_nn = ThreeNN.apply
+class _Interpolate(Function):
+    """three_interpolate: out[b,c,p] = sum_j weight[b,p,j] * features[b,c,idx[b,p,j]] (pointnet2_utils.py:111-151)."""
 
-
-class ThreeInterpolate(Function):
     @staticmethod
     def forward(ctx, features, idx, weight):
         assert features.is_contiguous() and idx.is_contiguous() and weight.is_contiguous()
-        K = _kernels()
-        B, c, m = features.size()
-        n = idx.size(1)
-        ctx.three_interpolate_for_backward = (idx, weight, m)
-        out = torch.empty(B, c, n, dtype=features.dtype, device=features.device)
+        K, (B, c, m), n = _kernels(), features.shape, idx.shape[1]
+        out = features.new_empty(B, c, n)
         K.pn2_three_interpolate(features, idx, weight, B, c, m, n, out)
+        ctx.saved = (idx, weight, m)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        idx, weight, m = ctx.three_interpolate_for_backward
-        K = _kernels()
-        B, c, n = grad_out.size()
-        grad = torch.zeros(B, c, m, dtype=grad_out.dtype, device=grad_out.device)
+        idx, weight, m = ctx.saved
+        K, (B, c, n) = _kernels(), grad_out.shape
+        grad = grad_out.new_zeros(B, c, m)
         K.pn2_three_interpolate_grad(grad_out.contiguous(), idx, weight, B, c, n, m, grad)
         return grad, None, None
 
 
-three_interpolate = ThreeInterpolate.apply
-
-
-class GroupingOperation(Function):
-    @staticmethod
-    def forward(ctx, features, idx):
-        assert features.is_contiguous() and idx.is_contiguous()
-        K = _kernels()
-        B, nfeatures, nsample = idx.size()
-        _, C, N = features.size()
-        out = torch.empty(B, C, nfeatures, nsample, dtype=features.dtype, device=features.device)
-        K.pn2_group_points(features, idx, B, C, N, nfeatures, nsample, out)
-        ctx.for_backwards = (idx, N)
-        return out
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        idx, N = ctx.for_backwards
-        K = _kernels()
-        B, C, npoint, nsample = grad_out.size()
-        grad = torch.zeros(B, C, N, dtype=grad_out.dtype, device=grad_out.device)
-        K.pn2_group_points_grad(grad_out.contiguous(), idx, B, C, N, npoint, nsample, grad)
-        return grad, None
-
-
-grouping_operation = GroupingOperation.apply
-
-
-class BallQuery(Function):
-    @staticmethod
-    def forward(ctx, radius, nsample, xyz, new_xyz):
-        assert new_xyz.is_contiguous() and xyz.is_contiguous()
-        K = _kernels()
-        B, N, _ = xyz.size()
-        npoint = new_xyz.size(1)
-        idx = _i32(K, B, npoint, nsample)
-        K.pn2_ball_query(new_xyz, xyz, B, N, npoint, radius, nsample, idx)
-        return idx
-
-    @staticmethod
-    def backward(ctx, a=None):
-        return None, None, None, None
-
-
-ball_query = BallQuery.apply
+def three_interpolate(features, idx, weight):
+    return _Interpolate.apply(features, idx, weight)
 
 
 class QueryAndGroup(nn.Module):            # pointnet2_utils.py:231-264
