@@ -57,13 +57,18 @@ int hcm_tc_conv_rowcat_supported(int Cout, int ks, int stride);
 /* flags bit 0 clear: pack w[Cout][Cin][ks][ks] for the forward conv; set: pack the same tensor for its data gradient seen as
  * a conv with Cin' = Cout(w), Cout' = Cin(w) (pass those as Cin, Cout).  flags bit 2 (4): row-concatenated layout, required iff
  * hcm_tc_conv_rowcat_supported(Cout, ks, stride of the consuming conv).  ldw > 0: `w` is a column block
- * of a wider [O][ldw][ks][ks] tensor (per-branch blocks of the 1x1 projection); lddw likewise for hcm_tc_wgrad */
+ * of a wider [O][ldw][ks][ks] tensor (per-branch blocks of the 1x1 projection); lddw likewise for hcm_tc_wgrad.
+ * 0 < ldw < Cin (forward packs) / 0 < lddw < Cin (hcm_tc_wgrad): the weight tensor has only ldw input channels and the input is
+ * stored with its channels zero-padded to Cin (the 3-channel stem on 4-channel rows, hcm_nchw_to_nhwc_pad): the GEMM's K is
+ * zero-padded, the gradient of the padding channels is dropped */
 int hcm_tc_conv_pack(const float* w, int ldw, void* wpack, int B, int H, int W, int Cin, int Cout, int ks, int flags,
                      cudaStream_t stream);
 /* all weight packs of a step in one launch: jobs (device) = njobs x 8 int64 {w ptr, out ptr, Cin, Cout, ks, mode, ldw, first_step};
  * mode 0/1 = hcm_tc_conv_pack(transpose 0/1), 2 = hcm_tc_dgrad_s2_pack, (Cin, Cout) as passed to those calls */
 int hcm_tc_pack_batch(const long long* jobs, int njobs, int total_steps, cudaStream_t stream);
-/* y[B,Ho,Wo,Cout] (+)= conv(T(x[B,H,W,Cin])) (+bias), 3x3 stride 1|2 or 1x1, pad (ks-1)/2 */
+/* y[B,Ho,Wo,Cout] (+)= conv(T(x[B,H,W,Cin])) (+bias), 3x3 stride 1|2 or 1x1, pad (ks-1)/2.  accumulate = 1 adds onto y with one
+ * vector reduction per element at the L2 (red.global.add.v4.f32: each element has exactly one writer per launch, the result is the
+ * same single fp32 addition; subnormal sums flush to zero) */
 int hcm_tc_conv(const float* x, const void* wpack, const float* bias, float* y, int B, int H, int W, int Cin, int Cout,
                 int ks, int stride, const float* in_scale, const float* in_shift, int in_relu, int accumulate,
                 cudaStream_t stream);
