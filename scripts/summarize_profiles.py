@@ -87,7 +87,7 @@ if os.path.exists(tj):
     traffic = json.load(open(tj))
 for rep in sorted(glob.glob(os.path.join(go, "*.ncu-rep"))):
     base = os.path.basename(rep).replace(".ncu-rep", "")
-    dst = base if base.startswith(tag) else tag + "_" + base
+    dst = base if base[:1] == "r" and base[1:3].isdigit() else tag + "_" + base
     ncu_rep(rep, os.path.join(out_dir, dst + ".txt"), base)
     rows, ci = rep_rows(rep)
     for frag, kern, key in TRAFFIC_KEYS:
