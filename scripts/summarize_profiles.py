@@ -69,11 +69,13 @@ def to_bytes(v, unit):
 TRAFFIC_KEYS = [
     ("tcconv18_b64", "tc_conv_kernel", "tc_conv 64x64 18->18 k3 s1 B=64"),
     ("tcwgrad18_b64", "tc_wgrad2_kernel", "tc_wgrad 64x64 18->18 k3 s1 B=64"),
-    ("tcconv144_b64", "tc_conv_kernel", "tc_conv 8x8 144->144 k3 s1 B=64"),
+    ("tcconv144", "tc_conv_kernel", "tc_conv 8x8 144->144 k3 s1 B=64"),
     ("nce_b64", "nce_logits_kernel", "nce_logits B=64"),
     ("nce_b64", "nce_bwd_kernel", "nce_bwd B=64"),
     ("dense_affinity", "dense_affinity_kernel<0>", "dense_affinity_fwd B=32"),
     ("dense_affinity", "dense_affinity_kernel<1>", "dense_affinity_bwd B=32"),
+    ("dense_v2", "dense_affinity_kernel<0>", "dense_affinity_fwd B=32"),
+    ("dense_v2", "dense_affinity_kernel<1>", "dense_affinity_bwd B=32"),
 ]
 
 for name in ("launches_b8.csv", "launches_b64.csv"):
